@@ -1,0 +1,37 @@
+"""Softmax attention plugin (reference: models/attention/softmax.py:14-127) on the flash-style tile kernel."""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..rpe import KERPLEPositionalEncoding
+from ._rotation import rotation_args
+from .base import BaseAttention
+
+
+class SoftmaxAttention(BaseAttention):
+    def __init__(self, dim: int, heads: int, dropout: float = 0.0, qkv_bias: bool = False):
+        super().__init__(dim, heads, dropout)
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.attn_dropout = nn.Dropout(dropout)  # kept for module-tree parity; the kernel applies it
+        self.proj_dropout = nn.Dropout(dropout)
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,
+                return_attention: bool = False):
+        if isinstance(rpe, KERPLEPositionalEncoding):  # softmax.py:69-77
+            raise NotImplementedError(
+                "KERPLE RPE is designed specifically for kernelized attention (FAVOR+/ReLU Performer) and "
+                "cannot be used with standard softmax attention. For softmax attention, use RoPE or "
+                "Circulant-STRING RPE instead.")
+        rot, gtab, ta, tb = rotation_args(rpe, x.shape, self.heads, self.head_dim)
+        qkv = self.qkv(x)
+        p = self.attn_dropout.p if self.training else 0.0
+        out, attn = ops.softmax_attention(qkv, self.heads, rot, gtab, ta, tb, mask, p,
+                                          ops.next_seed() if p > 0 else 0, return_attention)
+        out = self.proj_dropout(self.proj(out))
+        return (out, attn) if return_attention else out
+
+    def extra_repr(self) -> str:
+        return super().extra_repr() + ", complexity=O(N²)"

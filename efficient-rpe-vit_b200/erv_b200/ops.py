@@ -1,0 +1,331 @@
+"""torch.autograd bindings of the C-ABI kernels.  Tensors stay torch-owned: the
+functions below only hand data pointers, shapes and the current stream to liberv_b200.so."""
+import itertools
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _capi as C
+from ._capi import FEAT_FAVOR, FEAT_RELU, ROT_CIRCULANT, ROT_NONE, ROT_ROPE  # noqa: F401
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed() -> int:
+    """Host-side dropout seed: deterministic under torch.manual_seed, no device sync."""
+    return (torch.initial_seed() * 0x9E3779B1 + next(_seed_counter) * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def _split_dims(qkv: torch.Tensor, heads: int):
+    if qkv.dim() != 3 or qkv.shape[-1] % (3 * heads) != 0:
+        raise ValueError(f"qkv must be [B, N, 3*heads*head_dim], got {tuple(qkv.shape)} with heads={heads}")
+    b, n, c3 = qkv.shape
+    return b, n, c3 // 3 // heads
+
+
+# ---- tables -------------------------------------------------------------------------------------------
+class _CirculantTable(torch.autograd.Function):
+    """coeffs [H, K, Dh], positions [N-1, K] -> g [H, N, Dh] (row 0 = identity for the CLS token)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, coeffs, positions):
+        C.require_cuda(coeffs, positions)
+        coeffs = coeffs.to(torch.float32)
+        h, k, dh = coeffs.shape
+        n = positions.shape[0] + 1
+        coeffs, positions = coeffs.contiguous(), positions.to(coeffs.device, torch.float32).contiguous()
+        g = torch.empty(h, n, dh, device=coeffs.device, dtype=torch.float32)
+        C.check(C.load().erv_circulant_table_fwd(C.ptr(coeffs), C.ptr(positions), h, n, dh, k, C.ptr(g), C.stream()),
+                "circulant_table")
+        ctx.save_for_backward(coeffs, positions)
+        return g
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dg):
+        coeffs, positions = ctx.saved_tensors
+        h, k, dh = coeffs.shape
+        n = positions.shape[0] + 1
+        lib = C.load()
+        dg = dg.to(torch.float32).contiguous().clone()  # the kernel folds slots in place
+        dc = torch.empty_like(coeffs)
+        nbytes = lib.erv_circulant_table_bwd_scratch(h, n, dh, k)
+        scratch = C.workspace(nbytes, coeffs.device)
+        C.check(lib.erv_circulant_table_bwd(C.ptr(coeffs), C.ptr(positions), C.ptr(dg), 1, h, n, dh, k, C.ptr(dc),
+                                            C.ptr(scratch), nbytes, C.stream()), "circulant_table_bwd")
+        return dc, None
+
+
+def circulant_table(coeffs, positions):
+    return _CirculantTable.apply(coeffs, positions)
+
+
+def rope_table(theta: float, num_patches: int, head_dim: int, device):
+    cos = torch.empty(num_patches, head_dim // 2, device=device, dtype=torch.float32)
+    sin = torch.empty_like(cos)
+    C.require_cuda(cos)
+    C.check(C.load().erv_rope_table(float(theta), num_patches, head_dim, C.ptr(cos), C.ptr(sin), C.stream()), "rope_table")
+    return cos, sin
+
+
+class _Rotate(torch.autograd.Function):
+    """Stand-alone rotation of x [B,H,N,Dh]; tab_a/tab_b as in erv_rotate()."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, rot, tab_a, tab_b):
+        C.require_cuda(x, tab_a, tab_b)
+        x = x.to(torch.float32).contiguous()
+        b, h, n, dh = x.shape
+        y = torch.empty_like(x)
+        tab_a = tab_a.to(torch.float32).contiguous()
+        tab_b = None if tab_b is None else tab_b.to(torch.float32).contiguous()
+        C.check(C.load().erv_rotate(C.ptr(x), C.ptr(y), b, h, n, dh, rot, C.ptr(tab_a), C.ptr(tab_b), 0, C.stream()), "rotate")
+        ctx.rot = rot
+        ctx.save_for_backward(x, tab_a, tab_b)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, tab_a, tab_b = ctx.saved_tensors
+        b, h, n, dh = x.shape
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        lib = C.load()
+        C.check(lib.erv_rotate(C.ptr(dy), C.ptr(dx), b, h, n, dh, ctx.rot, C.ptr(tab_a), C.ptr(tab_b), 1, C.stream()), "rotate_bwd")
+        dtab = None
+        if ctx.rot == ROT_CIRCULANT and ctx.needs_input_grad[2]:
+            dtab = torch.zeros_like(tab_a)
+            C.check(lib.erv_rotate_table_grad(C.ptr(x), C.ptr(dy), b, h, n, dh, C.ptr(dtab), C.stream()), "rotate_table_grad")
+        return dx, None, dtab, None
+
+
+def rotate(x, rot, tab_a, tab_b=None):
+    out = _Rotate.apply(x, rot, tab_a, tab_b)
+    return out.to(x.dtype)
+
+
+# ---- feature maps --------------------------------------------------------------------------------------
+class _FeatureMap(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, omega, kind):
+        C.require_cuda(x, omega)
+        x, omega = x.to(torch.float32).contiguous(), omega.to(torch.float32).contiguous()
+        b, h, n, dh = x.shape
+        m = omega.shape[-1]
+        lib = C.load()
+        phi = torch.empty(b, h, n, m, device=x.device, dtype=torch.float32)
+        nbytes = lib.erv_feature_map_workspace(h, dh, m)
+        ws = C.workspace(nbytes, x.device)
+        C.check(lib.erv_feature_map_fwd(C.ptr(x), C.ptr(omega), b, h, n, dh, m, kind, C.ptr(phi), C.ptr(ws), nbytes,
+                                        C.stream()), "feature_map")
+        ctx.kind = kind
+        ctx.save_for_backward(x, omega)
+        return phi
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dphi):
+        x, omega = ctx.saved_tensors
+        b, h, n, dh = x.shape
+        m = omega.shape[-1]
+        lib = C.load()
+        dphi = dphi.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        nbytes = lib.erv_feature_map_workspace(h, dh, m)
+        ws = C.workspace(nbytes, x.device)
+        C.check(lib.erv_feature_map_bwd(C.ptr(x), C.ptr(omega), C.ptr(dphi), b, h, n, dh, m, ctx.kind, C.ptr(dx),
+                                        C.ptr(ws), nbytes, C.stream()), "feature_map_bwd")
+        return dx, None, None
+
+
+def feature_map(x, omega, kind):
+    return _FeatureMap.apply(x, omega, kind)
+
+
+# ---- attention cores -----------------------------------------------------------------------------------
+class _LinearAttention(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, qkv, omega, gtab, heads, kind, rot, tab_a, tab_b):
+        # rot == CIRCULANT: gtab (differentiable) is the table; otherwise tab_a/tab_b (buffers)
+        C.require_cuda(qkv, omega)
+        qkv = qkv.contiguous()
+        b, n, dh = _split_dims(qkv, heads)
+        m = omega.shape[-1]
+        omega = _f32c(omega)
+        ta = _f32c(gtab) if rot == ROT_CIRCULANT else _f32c(tab_a)
+        tb = _f32c(tab_b)
+        lib = C.load()
+        out = torch.empty(b, n, heads * dh, device=qkv.device, dtype=qkv.dtype)
+        nbytes = lib.erv_linear_attention_workspace(b, n, heads, dh, m, rot, 0)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_linear_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(omega), b, n, heads, dh, m, kind, rot,
+                                             C.ptr(ta), C.ptr(tb), C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                "linear_attention")
+        ctx.meta = (b, n, heads, dh, m, kind, rot)
+        ctx.save_for_backward(qkv, out, omega, ta, tb)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        qkv, out, omega, ta, tb = ctx.saved_tensors
+        b, n, heads, dh, m, kind, rot = ctx.meta
+        lib = C.load()
+        dout = dout.to(qkv.dtype).contiguous()
+        dqkv = torch.empty_like(qkv)
+        dg_part = None
+        if rot == ROT_CIRCULANT:
+            slots = lib.erv_circulant_slots(b, heads)
+            dg_part = torch.empty(heads, slots, n, dh, device=qkv.device, dtype=torch.float32)
+        nbytes = lib.erv_linear_attention_workspace(b, n, heads, dh, m, rot, 1)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_linear_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(dout), C.ptr(dqkv), C.ptr(omega), b, n, heads,
+                                             dh, m, kind, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), C.dtype_code(qkv),
+                                             C.ptr(ws), nbytes, C.stream()), "linear_attention_bwd")
+        dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[2]) else None
+        return dqkv, None, dgtab, None, None, None, None, None
+
+
+def linear_attention(qkv, omega, heads, kind, rot=ROT_NONE, gtab=None, tab_a=None, tab_b=None):
+    return _LinearAttention.apply(qkv, omega, gtab, heads, kind, rot, tab_a, tab_b)
+
+
+class _KerpleAttention(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, qkv, omega, bias, heads, kind):
+        C.require_cuda(qkv, omega, bias)
+        qkv = qkv.contiguous()
+        b, n, dh = _split_dims(qkv, heads)
+        m = omega.shape[-1]
+        omega, bias = _f32c(omega), _f32c(bias)
+        lib = C.load()
+        out = torch.empty(b, n, heads * dh, device=qkv.device, dtype=qkv.dtype)
+        den = torch.empty(b, heads, n, device=qkv.device, dtype=torch.float32)
+        nbytes = lib.erv_kerple_attention_workspace(b, n, heads, dh, m, 0)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_kerple_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(omega), C.ptr(bias), b, n, heads,
+                                             dh, m, kind, C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                "kerple_attention")
+        ctx.meta = (b, n, heads, dh, m, kind)
+        ctx.save_for_backward(qkv, out, den, omega, bias)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        qkv, out, den, omega, bias = ctx.saved_tensors
+        b, n, heads, dh, m, kind = ctx.meta
+        lib = C.load()
+        dout = dout.to(qkv.dtype).contiguous()
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.empty_like(bias)
+        nbytes = lib.erv_kerple_attention_workspace(b, n, heads, dh, m, 1)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_kerple_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(dout), C.ptr(dqkv), C.ptr(dbias),
+                                             C.ptr(omega), C.ptr(bias), b, n, heads, dh, m, kind, C.dtype_code(qkv),
+                                             C.ptr(ws), nbytes, C.stream()), "kerple_attention_bwd")
+        return dqkv, None, dbias, None, None
+
+
+def kerple_attention(qkv, omega, bias, heads, kind):
+    return _KerpleAttention.apply(qkv, omega, bias, heads, kind)
+
+
+class _SoftmaxAttention(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, qkv, gtab, heads, rot, tab_a, tab_b, mask, dropout_p, seed, want_attn):
+        C.require_cuda(qkv, mask)
+        qkv = qkv.contiguous()
+        b, n, dh = _split_dims(qkv, heads)
+        ta = _f32c(gtab) if rot == ROT_CIRCULANT else _f32c(tab_a)
+        tb = _f32c(tab_b)
+        mask8 = None
+        if mask is not None:
+            if mask.dim() == 4:
+                if mask.shape[1] != 1:
+                    raise ValueError("mask must be [B, N, N] or [B, 1, N, N]")
+                mask = mask[:, 0]
+            mask8 = (mask != 0).expand(b, n, n).to(torch.uint8).contiguous()
+        lib = C.load()
+        out = torch.empty(b, n, heads * dh, device=qkv.device, dtype=qkv.dtype)
+        lse = torch.empty(b, heads, n, device=qkv.device, dtype=torch.float32)
+        attn = torch.empty(b, heads, n, n, device=qkv.device, dtype=torch.float32) if want_attn else None
+        nbytes = lib.erv_softmax_attention_workspace(b, n, heads, dh, rot, 0)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_softmax_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(attn), C.ptr(mask8), b, n, heads,
+                                              dh, rot, C.ptr(ta), C.ptr(tb), float(dropout_p), seed, C.dtype_code(qkv),
+                                              C.ptr(ws), nbytes, C.stream()), "softmax_attention")
+        ctx.meta = (b, n, heads, dh, rot, float(dropout_p), seed)
+        ctx.save_for_backward(qkv, out, lse, ta, tb, mask8)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+            return out, attn
+        return out, None
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout, _dattn):
+        qkv, out, lse, ta, tb, mask8 = ctx.saved_tensors
+        b, n, heads, dh, rot, p, seed = ctx.meta
+        lib = C.load()
+        dout = dout.to(qkv.dtype).contiguous()
+        dqkv = torch.empty_like(qkv)
+        dg_part = None
+        if rot == ROT_CIRCULANT:
+            slots = lib.erv_circulant_slots(b, heads)
+            dg_part = torch.empty(heads, slots, n, dh, device=qkv.device, dtype=torch.float32)
+        nbytes = lib.erv_softmax_attention_workspace(b, n, heads, dh, rot, 1)
+        ws = C.workspace(nbytes, qkv.device)
+        C.check(lib.erv_softmax_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(dout), C.ptr(dqkv), C.ptr(mask8),
+                                              b, n, heads, dh, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), p, seed,
+                                              C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()), "softmax_attention_bwd")
+        dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[1]) else None
+        return dqkv, dgtab, None, None, None, None, None, None, None, None
+
+
+def softmax_attention(qkv, heads, rot=ROT_NONE, gtab=None, tab_a=None, tab_b=None, mask=None, dropout_p=0.0,
+                      seed=0, want_attn=False):
+    return _SoftmaxAttention.apply(qkv, gtab, heads, rot, tab_a, tab_b, mask, dropout_p, seed, want_attn)
+
+
+# ---- Toeplitz product ----------------------------------------------------------------------------------
+class _Toeplitz(torch.autograd.Function):
+    """c [R, 2n-1], x [P, n, d]; batch p uses row p (R == P) or p % R."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, c, x):
+        C.require_cuda(c, x)
+        c, x = c.to(torch.float32).contiguous(), x.to(torch.float32).contiguous()
+        p, n, d = x.shape
+        y = torch.empty_like(x)
+        C.check(C.load().erv_toeplitz_matmul_fwd(C.ptr(c), C.ptr(x), C.ptr(y), p, c.shape[0], n, d, C.stream()), "toeplitz")
+        ctx.save_for_backward(c, x)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        c, x = ctx.saved_tensors
+        p, n, d = x.shape
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        dc = torch.empty_like(c) if ctx.needs_input_grad[0] else None
+        C.check(C.load().erv_toeplitz_matmul_bwd(C.ptr(c), C.ptr(x), C.ptr(dy), C.ptr(dx), C.ptr(dc), p, c.shape[0], n, d,
+                                                 C.stream()), "toeplitz_bwd")
+        return dc, dx
+
+
+def toeplitz_matmul(c, x):
+    return _Toeplitz.apply(c, x)

@@ -1,0 +1,103 @@
+"""The caller of the hot path: a small pre-norm ViT with injected attention / RPE plugins.
+
+Behaviourally equal to the reference's models/core/base_vit.py and models/components/unified_transformer.py
+(same module names -> same state_dict keys, same init laws), so reference checkpoints load.  Everything
+here is stock torch (Linear / LayerNorm / GELU run on cuBLAS / ATen); only `block.attention` is ours.
+"""
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+
+class UnifiedTransformerBlock(nn.Module):
+    """x + attn(norm1(x), rpe) ; x + mlp(norm2(x))   (unified_transformer.py:64-90)."""
+
+    def __init__(self, dim: int, attention: nn.Module, rpe: Optional[nn.Module] = None, mlp_dim: int = None,
+                 dropout: float = 0.0):
+        super().__init__()
+        self.dim = dim
+        self.mlp_dim = mlp_dim or dim * 4
+        self.attention = attention
+        self.rpe = rpe
+        self.mlp = nn.Sequential(nn.Linear(dim, self.mlp_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(self.mlp_dim, dim), nn.Dropout(dropout))
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x + self.attention(self.norm1(x), rpe=self.rpe)  # the RPE goes INTO the attention
+        return x + self.mlp(self.norm2(x))
+
+    def extra_repr(self) -> str:
+        return f"dim={self.dim}, mlp_dim={self.mlp_dim}, has_rpe={self.rpe is not None}"
+
+
+class BaseViT(nn.Module):
+    def __init__(self, image_size: int, in_channels: int, patch_size: int, num_classes: int, dim: int, depth: int,
+                 heads: int, mlp_dim: int, dropout: float = 0.1, attention_builder: Optional[Callable] = None,
+                 rpe_builder: Optional[Callable] = None):
+        super().__init__()
+        assert image_size % patch_size == 0, f"Image size {image_size} must be divisible by patch size {patch_size}"
+        assert dim % heads == 0, f"Model dimension {dim} must be divisible by number of heads {heads}"
+        if attention_builder is None:
+            raise ValueError("attention_builder must be provided")
+        self.image_size, self.patch_size, self.in_channels = image_size, patch_size, in_channels
+        self.num_classes, self.dim, self.depth, self.heads = num_classes, dim, depth, heads
+        self.mlp_dim, self.dropout = mlp_dim, dropout
+        self.num_patches = (image_size // patch_size) ** 2
+        self.patch_dim = in_channels * patch_size * patch_size
+
+        self.patch_embedding = nn.Linear(self.patch_dim, dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, self.num_patches + 1, dim))
+        blocks = []
+        for _ in range(depth):
+            attention = attention_builder(dim=dim, heads=heads, dropout=dropout)
+            # one RPE instance per block; the sequence has num_patches + 1 tokens (CLS)   base_vit.py:138-142
+            rpe = rpe_builder(num_patches=self.num_patches + 1, dim=dim, heads=heads) if rpe_builder else None
+            blocks.append(UnifiedTransformerBlock(dim, attention, rpe, mlp_dim, dropout))
+        self.transformer_blocks = nn.ModuleList(blocks)
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+        self._init_weights()
+
+    def _init_weights(self):  # base_vit.py:153-172
+        nn.init.normal_(self.pos_embedding, std=0.02)
+        nn.init.normal_(self.cls_token, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    def patchify(self, x: torch.Tensor) -> torch.Tensor:
+        """[B, C, H, W] -> [B, patches, C*p*p], patches in raster order (base_vit.py:174-198)."""
+        b, c, h, w = x.shape
+        assert c == self.in_channels, f"Expected {self.in_channels} channels, got {c}"
+        assert h == self.image_size and w == self.image_size, \
+            f"Expected {self.image_size}x{self.image_size} images, got {h}x{w}"
+        p = self.patch_size
+        x = x.reshape(b, c, h // p, p, w // p, p).permute(0, 2, 4, 1, 3, 5)
+        return x.reshape(b, self.num_patches, self.patch_dim)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.patch_embedding(self.patchify(x))
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding
+        for block in self.transformer_blocks:
+            x = block(x)
+        return self.mlp_head(x[:, 0])
+
+    def count_parameters(self) -> Dict[str, int]:
+        total = sum(p.numel() for p in self.parameters())
+        trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return {"total": total, "trainable": trainable, "non_trainable": total - trainable}
+
+    def get_attention_maps(self):
+        raise NotImplementedError("Attention map extraction must be implemented by specific model variants")
+
+    def extra_repr(self) -> str:
+        return (f"image_size={self.image_size}, patch_size={self.patch_size}, num_patches={self.num_patches}, "
+                f"dim={self.dim}, depth={self.depth}, heads={self.heads}")

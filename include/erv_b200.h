@@ -1,0 +1,163 @@
+/*
+ * erv_b200.h -- C ABI of the B200-native attention hot path of efficient-rpe-vit.
+ *
+ * The reference (alemassaad/efficient-rpe-vit) is pure Python: its "FFI" for this path is the
+ * plugin interface of models/attention/ and models/rpe/ (ATTENTION_REGISTRY, RPE_REGISTRY).  The
+ * host-side mirror of those classes lives in efficient-rpe-vit_b200/erv_b200/ and binds the entry
+ * points below with ctypes (erv_b200/_capi.py).  Each entry point names the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 ok, ERV_E_* otherwise; erv_last_error() gives a
+ *     thread-local message.  No exceptions, no allocation: outputs and workspaces are caller owned.
+ *   - all pointers are DEVICE pointers unless the name says host; `stream` is a cudaStream_t.
+ *   - `dtype` selects the element type of the activation tensors (qkv, out and their gradients):
+ *     ERV_F32 or ERV_BF16.  Parameters, tables, feature tensors and statistics are always fp32,
+ *     and all arithmetic accumulates in fp32.
+ *   - packed layout: qkv is the output of the reference's qkv Linear, [B, N, 3, H, Dh] contiguous
+ *     (favor_plus.py:174-176); q/k/v are read in place.  out is [B, N, H, Dh] == [B, N, C], i.e. the
+ *     layout after the reference's transpose(1,2).reshape (favor_plus.py:263).  dqkv mirrors qkv.
+ *   - re-entrant; the only global state is an atomic launch counter and per-function attributes.
+ */
+#ifndef ERV_B200_H
+#define ERV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERV_ABI_VERSION 1
+
+enum { ERV_OK = 0, ERV_E_INVALID = 1, ERV_E_UNSUPPORTED = 2, ERV_E_CUDA = 3, ERV_E_WORKSPACE = 4 };
+enum { ERV_F32 = 0, ERV_BF16 = 1 };
+enum { ERV_FEAT_FAVOR = 0, ERV_FEAT_RELU = 1 };                 /* favor_plus.py:112 / relu.py:116 */
+enum { ERV_ROT_NONE = 0, ERV_ROT_ROPE = 1, ERV_ROT_CIRCULANT = 2 }; /* rope.py:70 / circulant_string.py:297 */
+enum { ERV_PREP_SCALE = 0, ERV_PREP_L2NORM = 1, ERV_PREP_NONE = 2 }; /* favor_plus.py:187-209 */
+
+int erv_abi_version(void);
+const char* erv_last_error(void);
+/* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
+uint64_t erv_launch_count(void);
+void erv_reset_launch_count(void);
+
+/* ---- tables ------------------------------------------------------------------------------ */
+
+/* RoPE cos/sin caches [num_patches, Dh/2]; replaces RoPE.__init__ (rope.py:53-68). */
+int erv_rope_table(float theta, int num_patches, int head_dim, float* cos_out, float* sin_out, void* stream);
+
+/* Circulant-STRING rotation table.  For head h, token n (n=0 is CLS -> identity) the rotation
+ * of circulant_string.py:234-295 equals a circular convolution with g = Re IFFT(exp(i*theta)),
+ * theta[h,n,:] = 2*sum_k pos[n-1,k]*Im FFT(coeffs[h,k,:]).  g_out is [H, N, Dh].
+ * coeffs [H, coord_dim, Dh], positions [N-1, coord_dim]. */
+int erv_circulant_table_fwd(const float* coeffs, const float* positions, int H, int N, int head_dim,
+                            int coord_dim, float* g_out, void* stream);
+/* d coeffs from d g.  dg_part is [H, slots, N, Dh] (partial sums the attention backward kernels
+ * produce, one slot per CTA); they are summed here in a fixed order, in place into slot 0 (dg_part is
+ * clobbered).  scratch: erv_circulant_table_bwd_scratch() bytes, 8-byte aligned. */
+size_t erv_circulant_table_bwd_scratch(int H, int N, int head_dim, int coord_dim);
+int erv_circulant_table_bwd(const float* coeffs, const float* positions, float* dg_part, int slots, int H,
+                            int N, int head_dim, int coord_dim, float* dcoeffs, void* scratch,
+                            size_t scratch_bytes, void* stream);
+
+/* Stand-alone rotation of a [B, H, N, Dh] fp32 contiguous tensor: RoPE.apply_rotary_emb
+ * (rope.py:70-137; tab_a = cos, tab_b = sin, each [N, Dh/2], already gathered at `positions`) or
+ * CirculantStringRPE.apply_circulant_string (circulant_string.py:297-341; tab_a = g table).
+ * inverse != 0 applies the transpose (the backward of the rotation).  dg_accum (circulant,
+ * optional, [H, N, Dh], pre-zeroed) receives sum_b of the table gradient given x_raw. */
+int erv_rotate(const float* x, float* y, int B, int H, int N, int head_dim, int rot,
+               const float* tab_a, const float* tab_b, int inverse, void* stream);
+int erv_rotate_table_grad(const float* x_raw, const float* dy, int B, int H, int N, int head_dim,
+                          float* dg_accum, void* stream);
+
+/* ---- random-feature maps ----------------------------------------------------------------- */
+
+/* phi(x) for x [B, H, N, Dh] fp32 contiguous, omega [H, Dh, M]: FAVORPlusAttention._compute_phi_positive
+ * (favor_plus.py:112-140, per-token max subtracted) or ReLUAttention._compute_relu_features
+ * (relu.py:116-138).  phi_out [B, H, N, M].  workspace: erv_feature_map_workspace() bytes. */
+size_t erv_feature_map_workspace(int H, int head_dim, int M);
+int erv_feature_map_fwd(const float* x, const float* omega, int B, int H, int N, int head_dim, int M,
+                        int kind, float* phi_out, void* workspace, size_t workspace_bytes, void* stream);
+/* dx given dphi (the max is a constant, favor_plus.py:131). */
+int erv_feature_map_bwd(const float* x, const float* omega, const float* dphi, int B, int H, int N,
+                        int head_dim, int M, int kind, float* dx, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---- attention cores --------------------------------------------------------------------- */
+
+/* Workspace (bytes) needed by the *_fwd / *_bwd calls below for these shapes. */
+size_t erv_linear_attention_workspace(int B, int N, int H, int head_dim, int M, int rot, int backward);
+size_t erv_kerple_attention_workspace(int B, int N, int H, int head_dim, int M, int backward);
+size_t erv_softmax_attention_workspace(int B, int N, int H, int head_dim, int rot, int backward);
+/* number of circulant partial-gradient slots the backward kernels write (see circulant_table_bwd) */
+int erv_circulant_slots(int B, int H);
+
+/* FAVOR+/ReLU linear attention without KERPLE (favor_plus.py:179-260 else-branch, relu.py:177-258):
+ *   x = rot(q|k) * Dh^-1/4 ; phi ; out = phi(q) (phi(k)^T v) / (phi(q) sum_n phi(k) + 1e-6).
+ * omega [H, Dh, M].  rot tables as in erv_rotate (rope tables cover positions 0..N-1). */
+int erv_linear_attention_fwd(const void* qkv, void* out, const float* omega, int B, int N, int H,
+                             int head_dim, int M, int kind, int rot, const float* tab_a,
+                             const float* tab_b, int dtype, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* Backward (replaces autograd over the ops above).  `out` is the saved forward
+ * output.  dg_part ([H, erv_circulant_slots, N, Dh], circulant only) is overwritten. */
+int erv_linear_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv,
+                             const float* omega, int B, int N, int H, int head_dim, int M, int kind,
+                             int rot, const float* tab_a, const float* tab_b, float* dg_part, int dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* KERPLE linear attention (favor_plus.py:197-245 + kerple.py:99-344 + fft_utils.py:112-172), evaluated
+ * as Toeplitz-masked attention: A = (phi(q) phi(k)^T) * exp(bias[j-i+N-1]); out = A v / (A 1 + 1e-6)
+ * with q, k L2-normalised.  rel_pos_bias [H, 2N-1].  den_out [B, H, N] is saved for the backward. */
+int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_out, const float* omega,
+                             const float* rel_pos_bias, int B, int N, int H, int head_dim, int M,
+                             int kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int erv_kerple_attention_bwd(const void* qkv, const void* out, const float* den, const void* dout,
+                             void* dqkv, float* dbias, const float* omega, const float* rel_pos_bias,
+                             int B, int N, int H, int head_dim, int M, int kind, int dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Softmax attention (softmax.py:86-115): out = dropout(softmax(rot(q) rot(k)^T / sqrt(Dh) + mask)) v.
+ * mask: optional uint8 [B, N, N] (0 = masked, softmax.py:104-108), may be NULL.
+ * dropout_p in [0,1): attention-probability dropout (softmax.py:112) from a counter-based generator
+ * keyed by (seed, b, h, i, j) so the backward regenerates it.
+ * lse_out [B, H, N] (log-sum-exp, saved for backward).  attn_out: optional [B, H, N, N] fp32 dump of the
+ * (post-dropout) probabilities for return_attention=True (softmax.py:122-123), may be NULL. */
+int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_out, float* attn_out,
+                              const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
+                              const float* tab_a, const float* tab_b, float dropout_p, uint64_t seed,
+                              int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int erv_softmax_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout,
+                              void* dqkv, const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
+                              const float* tab_a, const float* tab_b, float* dg_part, float dropout_p,
+                              uint64_t seed, int dtype, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* ---- Toeplitz product -------------------------------------------------------------------- */
+
+/* y[p] = T(c[p % c_count]) x[p], T[i,j] = c[j-i+n-1]; replaces fft_toeplitz_matmul
+ * (fft_utils.py:17-172).  x, y: [P, n, d] fp32; c: [c_count, 2n-1] with P % c_count == 0 and batch p
+ * using coefficient row p % c_count when c_per_batch == 0 (shared/per-head rows), or row p when
+ * c_count == P. */
+int erv_toeplitz_matmul_fwd(const float* c, const float* x, float* y, int P, int c_count, int n, int d,
+                            void* stream);
+/* dx = T^T dy ; dc[r, delta] = sum_{p: row r} sum_{j-i=delta} dy[p,i,:] . x[p,j,:] */
+int erv_toeplitz_matmul_bwd(const float* c, const float* x, const float* dy, float* dx, float* dc,
+                            int P, int c_count, int n, int d, void* stream);
+
+/* ---- training-loop helpers ------------------------------------ */
+
+/* Fused Adam/AdamW over one flat fp32 parameter buffer (torch.optim.Adam semantics,
+ * experiments/utils/training.py:304-309).  grad_scale multiplies the gradient first (1/world_size after
+ * the data-parallel allreduce).  step is the 1-based step count, read from the DEVICE pointer step_dev
+ * (int64) if non-NULL -- so a captured CUDA graph can advance it -- else from the argument. */
+int erv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
+                  float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERV_B200_H */
