@@ -1,6 +1,10 @@
 // Library-wide state (thread-local error text, launch counter) and the flat fused Adam step.
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "erv_common.cuh"
 
 namespace erv {
@@ -13,6 +17,22 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+cudaError_t ensure_smem(const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> seen;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(fn, dev);
+  auto it = seen.find(key);
+  if (it != seen.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) seen[key] = bytes;
+  return e;
 }
 
 // torch.optim.Adam / AdamW semantics (no amsgrad, no maximize):

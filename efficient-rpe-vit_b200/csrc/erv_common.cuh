@@ -49,10 +49,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Opt a kernel in to > 48 KB of dynamic shared memory (cached per function by the caller).
+// Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute is set once per (function, device) and
+// only raised, so steady-state launches (and CUDA-graph capture) make no driver call here.
+cudaError_t ensure_smem(const void* fn, size_t bytes);
 template <typename K>
 inline cudaError_t allow_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return ensure_smem((const void*)kernel, bytes);
 }
 constexpr size_t kMaxSmem = 227 * 1024;
 

@@ -10,6 +10,27 @@ from ._capi import FEAT_FAVOR, FEAT_RELU, ROT_CIRCULANT, ROT_NONE, ROT_ROPE  # n
 
 _seed_counter = itertools.count(1)
 
+# bench.py sets this to a dict to time the attention C calls with CUDA events on the launching stream
+# ({name: [(start, end), ...]}); None (default) adds no work.
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.key, []).append((self.e0, e1))
+        return False
+
 
 def next_seed() -> int:
     """Host-side dropout seed: deterministic under torch.manual_seed, no device sync."""
@@ -167,9 +188,10 @@ class _LinearAttention(torch.autograd.Function):
         out = torch.empty(b, n, heads * dh, device=qkv.device, dtype=qkv.dtype)
         nbytes = lib.erv_linear_attention_workspace(b, n, heads, dh, m, rot, 0)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_linear_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(omega), b, n, heads, dh, m, kind, rot,
-                                             C.ptr(ta), C.ptr(tb), C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
-                "linear_attention")
+        with _timed("linear_attention_fwd"):
+            C.check(lib.erv_linear_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(omega), b, n, heads, dh, m, kind, rot,
+                                                 C.ptr(ta), C.ptr(tb), C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                    "linear_attention")
         ctx.meta = (b, n, heads, dh, m, kind, rot)
         ctx.save_for_backward(qkv, out, omega, ta, tb)
         return out
@@ -188,9 +210,10 @@ class _LinearAttention(torch.autograd.Function):
             dg_part = torch.empty(heads, slots, n, dh, device=qkv.device, dtype=torch.float32)
         nbytes = lib.erv_linear_attention_workspace(b, n, heads, dh, m, rot, 1)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_linear_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(dout), C.ptr(dqkv), C.ptr(omega), b, n, heads,
-                                             dh, m, kind, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), C.dtype_code(qkv),
-                                             C.ptr(ws), nbytes, C.stream()), "linear_attention_bwd")
+        with _timed("linear_attention_bwd"):
+            C.check(lib.erv_linear_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(dout), C.ptr(dqkv), C.ptr(omega), b, n, heads,
+                                                 dh, m, kind, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), C.dtype_code(qkv),
+                                                 C.ptr(ws), nbytes, C.stream()), "linear_attention_bwd")
         dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[2]) else None
         return dqkv, None, dgtab, None, None, None, None, None
 
@@ -213,9 +236,10 @@ class _KerpleAttention(torch.autograd.Function):
         den = torch.empty(b, heads, n, device=qkv.device, dtype=torch.float32)
         nbytes = lib.erv_kerple_attention_workspace(b, n, heads, dh, m, 0)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_kerple_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(omega), C.ptr(bias), b, n, heads,
-                                             dh, m, kind, C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
-                "kerple_attention")
+        with _timed("kerple_attention_fwd"):
+            C.check(lib.erv_kerple_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(omega), C.ptr(bias), b, n, heads,
+                                                 dh, m, kind, C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                    "kerple_attention")
         ctx.meta = (b, n, heads, dh, m, kind)
         ctx.save_for_backward(qkv, out, den, omega, bias)
         return out
@@ -231,9 +255,10 @@ class _KerpleAttention(torch.autograd.Function):
         dbias = torch.empty_like(bias)
         nbytes = lib.erv_kerple_attention_workspace(b, n, heads, dh, m, 1)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_kerple_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(dout), C.ptr(dqkv), C.ptr(dbias),
-                                             C.ptr(omega), C.ptr(bias), b, n, heads, dh, m, kind, C.dtype_code(qkv),
-                                             C.ptr(ws), nbytes, C.stream()), "kerple_attention_bwd")
+        with _timed("kerple_attention_bwd"):
+            C.check(lib.erv_kerple_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(den), C.ptr(dout), C.ptr(dqkv), C.ptr(dbias),
+                                                 C.ptr(omega), C.ptr(bias), b, n, heads, dh, m, kind, C.dtype_code(qkv),
+                                                 C.ptr(ws), nbytes, C.stream()), "kerple_attention_bwd")
         return dqkv, None, dbias, None, None
 
 
@@ -263,9 +288,10 @@ class _SoftmaxAttention(torch.autograd.Function):
         attn = torch.empty(b, heads, n, n, device=qkv.device, dtype=torch.float32) if want_attn else None
         nbytes = lib.erv_softmax_attention_workspace(b, n, heads, dh, rot, 0)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_softmax_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(attn), C.ptr(mask8), b, n, heads,
-                                              dh, rot, C.ptr(ta), C.ptr(tb), float(dropout_p), seed, C.dtype_code(qkv),
-                                              C.ptr(ws), nbytes, C.stream()), "softmax_attention")
+        with _timed("softmax_attention_fwd"):
+            C.check(lib.erv_softmax_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(attn), C.ptr(mask8), b, n, heads,
+                                                  dh, rot, C.ptr(ta), C.ptr(tb), float(dropout_p), seed, C.dtype_code(qkv),
+                                                  C.ptr(ws), nbytes, C.stream()), "softmax_attention")
         ctx.meta = (b, n, heads, dh, rot, float(dropout_p), seed)
         ctx.save_for_backward(qkv, out, lse, ta, tb, mask8)
         if want_attn:
@@ -287,9 +313,10 @@ class _SoftmaxAttention(torch.autograd.Function):
             dg_part = torch.empty(heads, slots, n, dh, device=qkv.device, dtype=torch.float32)
         nbytes = lib.erv_softmax_attention_workspace(b, n, heads, dh, rot, 1)
         ws = C.workspace(nbytes, qkv.device)
-        C.check(lib.erv_softmax_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(dout), C.ptr(dqkv), C.ptr(mask8),
-                                              b, n, heads, dh, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), p, seed,
-                                              C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()), "softmax_attention_bwd")
+        with _timed("softmax_attention_bwd"):
+            C.check(lib.erv_softmax_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(dout), C.ptr(dqkv), C.ptr(mask8),
+                                                  b, n, heads, dh, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), p, seed,
+                                                  C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()), "softmax_attention_bwd")
         dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[1]) else None
         return dqkv, dgtab, None, None, None, None, None, None, None, None
 

@@ -1,0 +1,105 @@
+"""Data-parallel training step around the attention hot path.
+
+One process per GPU, full model replica, batch sharded by rank.  Parameters and gradients live in two
+flat fp32 buffers, so a step is: forward, backward, ONE all-reduce of the flat gradient over NCCL (NVLink 5 /
+NVSwitch; skipped for world_size 1), ONE fused Adam kernel (erv_adam_step).  The whole step can be captured
+in a CUDA graph, which removes the per-op launch latency that dominates at the reference's tiny dims.
+
+The reference trains with torch.optim.Adam(lr=1e-3) on CrossEntropy (experiments/utils/training.py:53-69,
+304-309) in a single process; its per-step .item() syncs are not reproduced -- step() returns a device tensor.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _capi as C
+
+
+class Trainer:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, decoupled_weight_decay: bool = False, use_graph: bool = True,
+                 autocast_dtype: Optional[torch.dtype] = None, process_group=None):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.weight_decay, self.decoupled = weight_decay, decoupled_weight_decay
+        self.autocast_dtype = autocast_dtype
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        C.require_cuda(self.params[0])
+        sizes = [p.numel() for p in self.params]
+        total = sum(sizes)
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.gflat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p, n in zip(self.params, sizes):  # parameters and their .grad become views of the flat buffers
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)
+            p.grad = self.gflat[off:off + n].view_as(p)
+            off += n
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
+        if self.world > 1:  # identical replicas: rank 0's parameters and buffers win
+            dist.broadcast(self.flat, src=0, group=self.group)
+            for b in model.buffers():
+                dist.broadcast(b, src=0, group=self.group)
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+
+    # ---- one optimisation step on device-resident inputs -------------------------------------------------
+    def _step_impl(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        self.gflat.zero_()
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                logits = self.model(images)
+        else:
+            logits = self.model(images)
+        loss = F.cross_entropy(logits.float(), labels)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.gflat, group=self.group)
+        self.step_count += 1
+        C.check(C.load().erv_adam_step(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
+                                       self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                       self.weight_decay, int(self.decoupled), 1.0 / self.world, 0,
+                                       C.ptr(self.step_count), C.stream()), "adam_step")
+        return loss.detach()
+
+    def _capture(self, images: torch.Tensor, labels: torch.Tensor):
+        self._static = (torch.empty_like(images), torch.empty_like(labels))
+        self._static[0].copy_(images)
+        self._static[1].copy_(labels)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream: allocator, cuBLAS handles, lazy kernel loads
+            for _ in range(3):
+                self._step_impl(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        C.reset_launch_count()
+        with torch.cuda.graph(self._graph):
+            self._loss = self._step_impl(*self._static)
+        self.graph_kernels = C.launch_count()  # erv kernels recorded in the graph = launched per replay
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """images/labels may be CUDA tensors or pinned host tensors (copied asynchronously).  Returns the loss as
+        a device tensor (no host sync)."""
+        if not self.use_graph:
+            return self._step_impl(images.to(self.flat.device, non_blocking=True),
+                                   labels.to(self.flat.device, non_blocking=True))
+        if self._graph is None:
+            self._capture(images.to(self.flat.device), labels.to(self.flat.device))
+        self._static[0].copy_(images, non_blocking=True)
+        self._static[1].copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._loss
+
+    def kernels_per_step(self) -> Optional[int]:
+        """erv kernels launched per step in graph mode (counted while the graph was recorded)."""
+        return getattr(self, "graph_kernels", None)

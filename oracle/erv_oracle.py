@@ -243,8 +243,8 @@ def linear_attention_core(q, k, v, omega, kind: str, rpe_kind: Optional[str],
 
 
 def softmax_attention_core(q, k, v, rpe_kind: Optional[str], rpe=None, mask=None,
-                           return_attention: bool = False):
-    """softmax(q k^T / sqrt(Dh) [+mask]) v; softmax.py:86-115 (dropout off)."""
+                           return_attention: bool = False, dropout: float = 0.0):
+    """dropout(softmax(q k^T / sqrt(Dh) [+mask])) v; softmax.py:86-115."""
     if rpe_kind == "kerple":
         raise NotImplementedError("KERPLE RPE is designed specifically for kernelized attention")
     q, k = _rotate_qk(q, k, rpe_kind, rpe or {})
@@ -253,15 +253,16 @@ def softmax_attention_core(q, k, v, rpe_kind: Optional[str], rpe=None, mask=None
         if mask.dim() == 3:
             mask = mask.unsqueeze(1)
         s = s.masked_fill(mask == 0, float("-inf"))
-    p = s.softmax(dim=-1)
+    p = F.dropout(s.softmax(dim=-1), dropout, training=dropout > 0)
     out = p @ v
     return (out, p) if return_attention else out
 
 
 def attention_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], heads: int, kind: str,
                       rpe_kind: Optional[str] = None, rpe: Optional[Dict[str, torch.Tensor]] = None,
-                      mask=None, route: str = "fft"):
-    """One attention module, x [B,N,C] -> [B,N,C]: qkv Linear, core, proj Linear (dropout off).
+                      mask=None, route: str = "fft", dropout: float = 0.0):
+    """One attention module, x [B,N,C] -> [B,N,C]: qkv Linear, core, proj Linear, dropout (training only;
+    softmax.py:112,120, favor_plus.py:265).
 
     kind in {'softmax','favor','relu'}; rpe_kind in {None,'rope','circulant','kerple'}.
     """
@@ -269,11 +270,11 @@ def attention_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], heads: i
     qkv = F.linear(x, params["qkv.weight"], params.get("qkv.bias"))
     q, k, v = split_qkv(qkv, heads)
     if kind == "softmax":
-        o = softmax_attention_core(q, k, v, rpe_kind, rpe, mask)
+        o = softmax_attention_core(q, k, v, rpe_kind, rpe, mask, dropout=dropout)
     else:
         o = linear_attention_core(q, k, v, params["omega"], kind, rpe_kind, rpe, route)
     o = o.transpose(1, 2).reshape(b, n, c)
-    return F.linear(o, params["proj.weight"], params["proj.bias"])
+    return F.dropout(F.linear(o, params["proj.weight"], params["proj.bias"]), dropout, training=dropout > 0)
 
 
 # --------------------------------------------------------------------------------------
@@ -305,9 +306,9 @@ def patchify(img: torch.Tensor, p: int) -> torch.Tensor:
 
 
 def vit_forward(sd: Dict[str, torch.Tensor], images: torch.Tensor, model_name: str, cfg: dict,
-                route: str = "fft") -> torch.Tensor:
-    """Eval-mode forward of the reference model from its state_dict; base_vit.py:200-233 and
-    unified_transformer.py:64-90.  cfg needs patch_size, heads, depth, dim (+ rope theta)."""
+                route: str = "fft", dropout: float = 0.0) -> torch.Tensor:
+    """Forward of the reference model from its state_dict (eval mode when dropout == 0); base_vit.py:200-233
+    and unified_transformer.py:64-90.  cfg needs patch_size, heads, depth, dim (+ rope theta)."""
     attn_type, rpe_type = MODEL_VARIANTS[model_name]
     kind, rpe_kind = _ATTN_KIND[attn_type], _RPE_KIND[rpe_type]
     heads, dim = cfg["heads"], cfg["dim"]
@@ -321,10 +322,10 @@ def vit_forward(sd: Dict[str, torch.Tensor], images: torch.Tensor, model_name: s
         if rpe_kind == "rope":
             rpe["cos"], rpe["sin"] = rope_tables(n, dim // heads, cfg.get("theta", 10000.0), x.dtype)
         h = F.layer_norm(x, (dim,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
-        x = x + attention_forward(h, attn, heads, kind, rpe_kind, rpe, route=route)
+        x = x + attention_forward(h, attn, heads, kind, rpe_kind, rpe, route=route, dropout=dropout)
         h = F.layer_norm(x, (dim,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
-        h = F.gelu(F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"]))
-        x = x + F.linear(h, sd[pre + "mlp.3.weight"], sd[pre + "mlp.3.bias"])
+        h = F.dropout(F.gelu(F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"])), dropout, training=dropout > 0)
+        x = x + F.dropout(F.linear(h, sd[pre + "mlp.3.weight"], sd[pre + "mlp.3.bias"]), dropout, training=dropout > 0)
     h = F.layer_norm(x[:, 0], (dim,), sd["mlp_head.0.weight"], sd["mlp_head.0.bias"])
     return F.linear(h, sd["mlp_head.1.weight"], sd["mlp_head.1.bias"])
 
@@ -379,18 +380,19 @@ def trainable_keys(sd: Dict[str, torch.Tensor]):
 
 
 class CpuTrainer:
-    """The reference's training step on CPU: forward, CrossEntropy, backward, Adam(lr=1e-3)
-    (experiments/utils/training.py:53-69,304-309).  Dropout is left at 0 (its cost is
-    negligible beside the attention path); used only as the reported CPU baseline."""
+    """The reference's training step on CPU: forward (train mode, dropout as configured), CrossEntropy,
+    backward, Adam(lr=1e-3) (experiments/utils/training.py:53-69,304-309).  Used only as the reported CPU
+    baseline."""
 
     def __init__(self, model_name: str, cfg: dict, seed: int = 0, lr: float = 1e-3):
         self.model_name, self.cfg = model_name, cfg
+        self.dropout = float(cfg.get("dropout", 0.0))
         self.sd = init_state(model_name, cfg, seed)
         self.params = [self.sd[k].requires_grad_(True) for k in trainable_keys(self.sd)]
         self.opt = torch.optim.Adam(self.params, lr=lr)
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> float:
-        logits = vit_forward(self.sd, images, self.model_name, self.cfg)
+        logits = vit_forward(self.sd, images, self.model_name, self.cfg, dropout=self.dropout)
         loss = F.cross_entropy(logits, labels)
         self.opt.zero_grad()
         loss.backward()
