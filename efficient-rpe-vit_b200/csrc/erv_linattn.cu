@@ -427,6 +427,12 @@ extern "C" size_t erv_linear_attention_workspace(int B, int N, int H, int head_d
   return wt_bytes(H, head_dim, M);
 }
 
+namespace erv {  // tensor-core path (erv_linattn_tc.cu)
+bool la_tc_eligible(int N, int DH, int M);
+int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
+                  const float* ta, const float* tb, int dtype, cudaStream_t st);
+}  // namespace erv
+
 static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, void* dqkv, const float* omega, int B,
                      int N, int H, int DH, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part,
                      int dtype, void* ws, size_t ws_bytes, void* stream) {
@@ -441,6 +447,8 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   ERV_CHECK_ARG(!(bwd && rot == ERV_ROT_CIRCULANT) || dg_part, "%s: dg_part missing", fn);
   if (ws_bytes < wt_bytes(H, DH, M)) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (!bwd && la_tc_eligible(N, DH, M))
+    return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
   LaArgs a;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.wt = (const float*)ws; a.ta = ta; a.tb = tb;
   a.dg_part = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;

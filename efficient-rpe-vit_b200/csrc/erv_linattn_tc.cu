@@ -1,0 +1,427 @@
+// Tensor-core (tcgen05 + TMEM) FAVOR+/ReLU linear attention for head_dim 8/16, num_features <= 256.
+//
+// One persistent CTA (128 threads = 128 TMEM lanes) per SM walks (batch, head) pairs; tokens go through 128-row
+// tiles, thread t owns token t of the tile:
+//   G1  P[t][f]      = x_t . w_f                     (K = Dh)      3xTF32: x_hi w_hi + x_lo w_hi + x_hi w_lo
+//       phi          = exp(P - max_f P - |x|^2/2)/sqrt(M)  or  relu(P)/sqrt(M)   -- row max is thread-local
+//   G2  S[f][d]     += sum_t phi_k[t][f] [v|1][t][d]  (K = tokens)  phi in TF32, [v|1] split hi+lo
+//   G4  [num|den][t] = sum_f phi_q[t][f] S[f][.]      (K = features)
+// Accumulators live in TMEM (P: 256 columns, S: 2x32, num|den: 32); operands are written to shared memory by the
+// owning threads in the no-swizzle K-major canonical layout (erv_umma.cuh).  The projection needs fp32-level
+// accuracy because it feeds exp(); rounding phi and S to TF32 is averaged over N*M terms and stays far below the
+// 1e-4 parity budget, the value rows are split hi+lo (tests/test_parity_gpu.py holds the kernel to 1e-4).
+#include <cuda_bf16.h>
+
+#include "erv_common.cuh"
+#include "erv_umma.cuh"
+
+namespace erv {
+using namespace umma;
+
+struct LaTcArgs {
+  const void* qkv;
+  void* out;
+  const float* omega;  // [H][DH][M]
+  const float* ta;
+  const float* tb;
+  int B, N, H, M, Mp16, kind, rot;
+  float prescale, inv_sqrt_m;
+};
+
+template <int DH>
+struct TcCfg {
+  static constexpr int ND = (DH + 1 + 15) / 16 * 16;        // columns of [v|1] and [S|z], padded for the MMA N dim
+  static constexpr uint32_t X_LBO = 128, X_SBO = (DH / 4) * 128;  // x / w images: rows x Dh
+  static constexpr uint32_t T_LBO = 144, T_SBO = 32 * 144;  // images whose K index is the 128 tokens (padded chunks)
+  static constexpr uint32_t P_LBO = 128, P_SBO = 32 * 128;  // phi image [128 tokens x 128 features]
+  static constexpr uint32_t X_BYTES = 16 * X_SBO;           // 128 rows
+  static constexpr uint32_t PHI_BYTES = 16 * T_SBO;         // >= 16 * P_SBO
+  static constexpr uint32_t V_BYTES = (ND / 8) * T_SBO;     // one [ND x 128 tokens] image
+  static constexpr int COL_S = 256, COL_O = 256 + 2 * ND;   // TMEM columns
+};
+
+__host__ __device__ inline uint32_t tc_w_bytes(int DH, int Mp16) { return (uint32_t)(Mp16 / 8) * (DH / 4) * 128; }
+__host__ __device__ inline uint32_t tc_s_bytes(int ND, int Mp16) { return (uint32_t)(ND / 8) * (Mp16 / 4) * 144; }
+
+template <typename T, int DH>
+__device__ __forceinline__ void load_row(const T* __restrict__ p, float (&x)[DH]) {
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    float4 v = ld4(p + 4 * c);
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+}
+
+// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
+template <int DH>
+__device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const float* __restrict__ ta,
+                                             const float* __restrict__ tb, int h, int n, int N, float prescale) {
+  if (rot == ERV_ROT_ROPE) {
+#pragma unroll
+    for (int m = 0; m < DH / 2; ++m) {
+      const float c = __ldg(ta + (size_t)n * (DH / 2) + m), s = __ldg(tb + (size_t)n * (DH / 2) + m);
+      const float xe = x[2 * m], xo = x[2 * m + 1];
+      x[2 * m] = xe * c - xo * s;
+      x[2 * m + 1] = xe * s + xo * c;
+    }
+  } else if (rot == ERV_ROT_CIRCULANT) {
+    float g[DH], y[DH];
+    load_row<float, DH>(ta + ((size_t)h * N + n) * DH, g);
+#pragma unroll
+    for (int a = 0; a < DH; ++a) {
+      float acc = 0.f;
+#pragma unroll
+      for (int b = 0; b < DH; ++b) acc = fmaf(g[(a - b) & (DH - 1)], x[b], acc);
+      y[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < DH; ++a) x[a] = y[a];
+  }
+#pragma unroll
+  for (int a = 0; a < DH; ++a) x[a] *= prescale;
+}
+
+// write one token row as the hi / lo TF32 images of a K-major [128 x DH] operand
+template <int DH>
+__device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const float (&x)[DH], int t) {
+  using C = TcCfg<DH>;
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = to_tf32(x[4 * c + e]);
+      lo[e] = to_tf32(x[4 * c + e] - hi[e]);
+    }
+    const uint32_t off = (uint32_t)(t >> 3) * C::X_SBO + c * C::X_LBO + (t & 7) * 16;
+    st4(reinterpret_cast<float*>(xh + off), make_float4(hi[0], hi[1], hi[2], hi[3]));
+    st4(reinterpret_cast<float*>(xl + off), make_float4(lo[0], lo[1], lo[2], lo[3]));
+  }
+}
+
+// split an fp32 value into two bf16 (hi + lo carries ~17 significant bits)
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// 8 consecutive values -> one 16-byte chunk in each of the hi / lo bf16 images
+__device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, uint32_t off, const float (&v)[8]) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+  *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+// Shared-memory images (bytes).  bf16 images use 16-byte chunks of 8 elements along the fast index f (or d) and 128
+// contiguous bytes per group of 8 tokens:  byte(t, f) = (f/8)*CH + (t/8)*128 + (t%8)*16 + (f%8)*2.
+// Read as an MN-major operand (rows f, K = t): SBO = CH, LBO = 128; as a K-major operand (rows t, K = f): SBO = 128,
+// LBO = CH.  The same image therefore feeds phi^T [v|1] and phi [S|z].
+constexpr uint32_t kTokCh = 16 * 128;  // chunk stride of images with 128 token rows
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
+  using C = TcCfg<DH>;
+  constexpr int ND = C::ND;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_a, bar_b;  // G1 completions / G2-G4 completions
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float n2_s[128];
+  __shared__ float mx_s[2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
+  const int Mp16 = p.Mp16, M = p.M, N = p.N;
+  const int FH = Mp16 / 2;            // features per thread of a row pair
+  const int nrb = (Mp16 + 127) / 128; // 128-feature row blocks of S
+  const uint32_t wbytes = tc_w_bytes(DH, Mp16);
+  // the G2 A operand always spans whole 128-feature row blocks, so the images are padded to nrb * 128 rows
+  const uint32_t phibytes = (uint32_t)nrb * 16 * kTokCh;
+  const uint32_t s_ch = (uint32_t)(Mp16 / 8) * 128;   // chunk stride of the [S|z] image (rows = features)
+  uint8_t* wh = smem;
+  uint8_t* wl = wh + wbytes;
+  uint8_t* xh = wl + wbytes;
+  uint8_t* xl = xh + C::X_BYTES;
+  uint8_t* phi1 = xl + C::X_BYTES;
+  uint8_t* phi2 = phi1 + phibytes;
+  uint8_t* vreg = phi2 + phibytes;                     // K pass: [2 buffers][hi, lo] of (ND/8)*kTokCh; Q pass: [S|z] hi, lo
+  const uint32_t vbytes = (uint32_t)(ND / 8) * kTokCh;
+  uint8_t* s1 = vreg;
+  uint8_t* s2 = vreg + (uint32_t)(ND / 8) * s_ch;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar_a, 1);
+    mbar_init(&bar_b, 1);
+    mbar_init_fence();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t ph_a = 0, ph_b = 0;
+  bool pending_b = false;
+
+  const T* qkv = static_cast<const T*>(p.qkv);
+  T* out = static_cast<T*>(p.out);
+  const size_t tok_stride = (size_t)3 * p.H * DH;
+  const uint32_t idesc_p = make_idesc(FMT_TF32, 128, Mp16, false, false);
+  const uint32_t idesc_g2 = make_idesc(FMT_BF16, 128, ND, true, true);
+  const uint32_t idesc_g4 = make_idesc(FMT_BF16, 128, ND, false, true);
+  const float kLog2e = 1.4426950408889634f;
+  int cur_h = -1;
+
+  for (int pair = blockIdx.x; pair < p.B * p.H; pair += gridDim.x) {
+    const int b = pair / p.H, h = pair % p.H;
+    if (h != cur_h) {  // stage W^T hi/lo TF32 images for this head: rows f, K = Dh
+      cur_h = h;
+      const float* om = p.omega + (size_t)h * DH * M;
+      for (int i = tid; i < Mp16 * DH; i += 256) {
+        const int d = i / Mp16, f = i % Mp16;
+        const float w = (f < M) ? __ldg(om + (size_t)d * M + f) : 0.f;
+        const float hi = to_tf32(w), lo = to_tf32(w - hi);
+        const uint32_t off = off_kmajor(f, d, 4, 4, C::X_LBO, C::X_SBO);
+        *reinterpret_cast<float*>(wh + off) = hi;
+        *reinterpret_cast<float*>(wl + off) = lo;
+      }
+    }
+    const T* qb = qkv + qkv_off(b, 0, 0, h, N, p.H, DH);
+    const T* kb = qkv + qkv_off(b, 0, 1, h, N, p.H, DH);
+    const T* vb = qkv + qkv_off(b, 0, 2, h, N, p.H, DH);
+
+    auto emit_out = [&](int n0) {  // out = num / (den + eps) for the tile starting at n0 (reads TMEM: all lanes)
+      float r[32];
+      tmem_ld32(tm + lane_off + C::COL_O, r);
+      const int n = n0 + row;
+      if (part == 0 && n < N) {
+        const float den = r[DH] + kEps;
+        T* ob = out + out_off(b, n, h, N, p.H, DH);
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c)
+          st4(ob + 4 * c, make_float4(r[4 * c] / den, r[4 * c + 1] / den, r[4 * c + 2] / den, r[4 * c + 3] / den));
+      }
+    };
+
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: keys -> S ; pass 1: queries -> out
+      int tile = 0;
+      for (int n0 = 0; n0 < N; n0 += 128, ++tile) {
+        const int n = n0 + row;
+        const bool valid = n < N;
+        const int nt = min(128, N - n0);
+        // ---- step 1: operand images of this tile
+        if (part == 0) {
+          float x[DH];
+          float n2 = 0.f;
+          if (valid) {
+            load_row<T, DH>((pass == 0 ? kb : qb) + (size_t)n * tok_stride, x);
+            prologue_row<DH>(x, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+#pragma unroll
+            for (int a = 0; a < DH; ++a) n2 = fmaf(x[a], x[a], n2);
+            n2 *= 0.5f;
+          } else {
+#pragma unroll
+            for (int a = 0; a < DH; ++a) x[a] = 0.f;
+          }
+          n2_s[row] = n2;
+          store_x_images<DH>(xh, xl, x, row);
+        } else if (pass == 0) {  // [v | 1] rows, double buffered across tiles
+          uint8_t* v1 = vreg + (uint32_t)(tile & 1) * 2 * vbytes;
+          uint8_t* v2 = v1 + vbytes;
+          float v[DH];
+          if (valid) {
+            load_row<T, DH>(vb + (size_t)n * tok_stride, v);
+          } else {
+#pragma unroll
+            for (int d = 0; d < DH; ++d) v[d] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < DH / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = v[8 * c + e];
+            store_split8(v1, v2, c * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ch);
+          }
+          const float ones[8] = {valid ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store_split8(v1, v2, (DH / 8) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ones);
+        }
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+        // ---- G1: P = x W^T, three TF32 terms
+        if (tid == 0) {
+          fence_after_sync();
+          bool acc = false;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint8_t* xa = (term == 1) ? xl : xh;
+            const uint8_t* wb = (term == 2) ? wl : wh;
+#pragma unroll
+            for (int s = 0; s < DH / 8; ++s) {
+              mma_tf32(tm, make_desc(smem_u32(xa) + s * 2 * C::X_LBO, C::X_LBO, C::X_SBO),
+                       make_desc(smem_u32(wb) + s * 2 * C::X_LBO, C::X_LBO, C::X_SBO), idesc_p, acc);
+              acc = true;
+            }
+          }
+          commit(&bar_a);
+        }
+        mbar_wait(&bar_a, ph_a);
+        ph_a ^= 1;
+        if (pending_b) {  // tensor-pipe work completes in order: the previous tile's G2/G4 is done as well
+          mbar_wait(&bar_b, ph_b);
+          ph_b ^= 1;
+          pending_b = false;
+          fence_after_sync();
+          if (pass == 1) emit_out(n0 - 128);
+        }
+        fence_after_sync();
+        // ---- row max over the real features (FAVOR+), two threads per row
+        const int fbeg = part * FH;
+        const float n2 = n2_s[row];
+        float mx = 0.f;
+        if (p.kind == ERV_FEAT_FAVOR) {
+          float m_part = -INFINITY;
+          for (int c0 = 0; c0 < FH; c0 += 8) {
+            uint32_t r[8];
+            tmem_ld8_nowait(tm + lane_off + fbeg + c0, r);
+            tmem_wait_ld8(r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (fbeg + c0 + i < M) m_part = fmaxf(m_part, __uint_as_float(r[i]));
+          }
+          mx_s[part][row] = m_part;
+          __syncthreads();
+          mx = fmaxf(mx_s[0][row], mx_s[1][row]);
+        }
+        // ---- phi for this thread's features -> hi/lo bf16 images
+        const float shift = mx + n2;
+        for (int c0 = 0; c0 < FH; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8_nowait(tm + lane_off + fbeg + c0, r);
+          tmem_wait_ld8(r);
+          float ph_v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pv = __uint_as_float(r[i]);
+            float v = 0.f;
+            if (valid && fbeg + c0 + i < M)
+              v = (p.kind == ERV_FEAT_FAVOR) ? exp2f(((pv - mx) - n2) * kLog2e) * p.inv_sqrt_m
+                                             : fmaxf(pv, 0.f) * p.inv_sqrt_m;
+            ph_v[i] = v;
+          }
+          store_split8(phi1, phi2, (uint32_t)((fbeg + c0) >> 3) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ph_v);
+        }
+        (void)shift;
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          fence_after_sync();
+          if (pass == 0) {  // G2: S[rb] (+)= phi^T [v|1], terms hi*hi + hi*lo + lo*hi
+            const uint8_t* v1 = vreg + (uint32_t)(tile & 1) * 2 * vbytes;
+            const uint8_t* v2 = v1 + vbytes;
+            const int ksteps = (nt + 15) / 16;
+            for (int rb = 0; rb < nrb; ++rb) {
+              bool acc = n0 > 0;
+              for (int term = 0; term < 3; ++term) {
+                const uint8_t* a_img = (term == 2) ? phi2 : phi1;
+                const uint8_t* b_img = (term == 1) ? v2 : v1;
+                for (int s = 0; s < ksteps; ++s) {
+                  mma_f16(tm + C::COL_S + rb * ND,
+                          make_desc(smem_u32(a_img) + (uint32_t)rb * 16 * kTokCh + s * 256, 128, kTokCh),
+                          make_desc(smem_u32(b_img) + s * 256, 128, kTokCh), idesc_g2, acc);
+                  acc = true;
+                }
+              }
+            }
+          } else {  // G4: [num|den] = phi [S|z]
+            bool acc = false;
+            for (int term = 0; term < 3; ++term) {
+              const uint8_t* a_img = (term == 2) ? phi2 : phi1;
+              const uint8_t* b_img = (term == 1) ? s2 : s1;
+              for (int s = 0; s < Mp16 / 16; ++s) {
+                mma_f16(tm + C::COL_O, make_desc(smem_u32(a_img) + (uint32_t)s * 2 * kTokCh, kTokCh, 128),
+                        make_desc(smem_u32(b_img) + s * 256, 128, s_ch), idesc_g4, acc);
+                acc = true;
+              }
+            }
+          }
+          commit(&bar_b);
+        }
+        pending_b = true;
+      }
+      // ---- end of pass: drain the tensor pipe
+      mbar_wait(&bar_b, ph_b);
+      ph_b ^= 1;
+      pending_b = false;
+      fence_after_sync();
+      if (pass == 0) {  // S (TMEM, lanes = features) -> [S|z] hi/lo bf16 images: byte(f, d) = (d/8)*s_ch + (f/8)*128 + (f%8)*16
+        float sv[32];
+        tmem_ld32(tm + lane_off + C::COL_S + (part < nrb ? part : 0) * ND, sv);
+        const int f = part * 128 + row;
+        if (part < nrb && f < Mp16) {
+#pragma unroll
+          for (int c = 0; c < ND / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
+            store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
+          }
+        }
+        fence_before_sync();
+      } else {
+        emit_out(((N - 1) / 128) * 128);
+        fence_before_sync();
+      }
+    }
+    __syncthreads();  // the next pair's [v|1] images overwrite the [S|z] images
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+size_t la_tc_smem_bytes(int DH, int Mp16) {
+  const int ND = (DH + 1 + 15) / 16 * 16;
+  const size_t x_bytes = 16 * (size_t)(DH / 4) * 128;
+  size_t v_bytes = 4 * (size_t)(ND / 8) * kTokCh;               // 2 buffers x (hi, lo)
+  const size_t s_bytes = 2 * (size_t)(ND / 8) * (Mp16 / 8) * 128;  // hi, lo
+  if (s_bytes > v_bytes) v_bytes = s_bytes;
+  const size_t nrb = (Mp16 + 127) / 128;
+  return 2 * (size_t)tc_w_bytes(DH, Mp16) + 2 * x_bytes + 2 * nrb * 16 * kTokCh + v_bytes + 128;
+}
+
+bool la_tc_eligible(int N, int DH, int M) {
+  static const bool disabled = getenv("ERV_DISABLE_TC") != nullptr;
+  return !disabled && (DH == 8 || DH == 16) && M <= 256 && N >= 33;
+}
+
+int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
+                  const float* ta, const float* tb, int dtype, cudaStream_t st) {
+  LaTcArgs a;
+  a.qkv = qkv; a.out = out; a.omega = omega; a.ta = ta; a.tb = tb;
+  a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = (M + 15) / 16 * 16; a.kind = kind; a.rot = rot;
+  a.prescale = (float)pow((double)DH, -0.25);
+  a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
+  const size_t smem = la_tc_smem_bytes(DH, a.Mp16);
+  int grid = (kNumSMs / H) * H;  // multiple of H: each CTA stays on one head (W images staged once)
+  if (grid < H) grid = H;
+  if (grid > B * H) grid = B * H;
+#define TC_LAUNCH(TT, D)                                                  \
+  do {                                                                    \
+    ERV_CUDA(allow_smem(la_tc_fwd_kernel<TT, D>, smem));                  \
+    la_tc_fwd_kernel<TT, D><<<grid, 256, smem, st>>>(a);                  \
+  } while (0)
+  if (dtype == ERV_F32) {
+    if (DH == 16) TC_LAUNCH(float, 16); else TC_LAUNCH(float, 8);
+  } else {
+    if (DH == 16) TC_LAUNCH(__nv_bfloat16, 16); else TC_LAUNCH(__nv_bfloat16, 8);
+  }
+#undef TC_LAUNCH
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
+
+}  // namespace erv

@@ -157,6 +157,14 @@ int erv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
                   float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
 
+/* ---- diagnostics -------------------------------------------------------------------------- */
+
+/* D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (TF32 or BF16 operands, fp32 accumulate in TMEM) using the shared-
+ * memory operand layouts of the fused kernels; *_mn_major selects MN-major instead of K-major.  Used by the GPU tests
+ * to pin the descriptor encodings. */
+int erv_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
+                        int bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
