@@ -275,12 +275,12 @@ __device__ __forceinline__ void h1_accum(float* __restrict__ S, const float* __r
 
 // R[t][j] = sum_{f<K} A[t][f] * B[f][j], j < 4*NJG.  A: feature tile (smem, stride lda), B: rows with stride ldb
 // (smem or global, 16-byte aligned).  Partials go to red[ks][TT][LDM]; on return red[0] holds R.
-// Contains barriers.  red must hold min(8, max(1, nthreads/items)) * TT * LDM floats.
+// Contains barriers.  red must hold min(6, max(1, nthreads/items)) * TT * LDM floats.
 template <int DH, int TT, int NJG>
 __device__ __forceinline__ int h2_kslices(int nthreads) {
   constexpr int ITEMS = (TT / 4) * NJG;
   int ks = nthreads / ITEMS;
-  return ks < 1 ? 1 : (ks > 8 ? 8 : ks);
+  return ks < 1 ? 1 : (ks > 6 ? 6 : ks);
 }
 
 template <int DH, int TT, int NJG>

@@ -52,10 +52,10 @@ __host__ __device__ inline LaSmem la_layout(int DH, int Mp, int ldp, int nthread
   L.pm = o; o += (nthreads / TT + 1) * TT;
   int items = (TT / 4) * (DH / 4 + 1);
   int ks = nthreads / items;
-  ks = ks < 1 ? 1 : (ks > 8 ? 8 : ks);
+  ks = ks < 1 ? 1 : (ks > 6 ? 6 : ks);
   int items2 = (TT / 4) * (DH / 4);
   int ks2 = nthreads / items2;
-  ks2 = ks2 < 1 ? 1 : (ks2 > 8 ? 8 : ks2);
+  ks2 = ks2 < 1 ? 1 : (ks2 > 6 ? 6 : ks2);
   L.red = o; o += (ks > ks2 ? ks : ks2) * tile;
   L.total = o;
   return L;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void features_bwd_tail(const LaArgs& p, const LaSmem&
 }
 
 template <typename T, int DH, int TT>
-__global__ void __launch_bounds__(320, 1) la_bwd_kernel(const LaArgs p) {
+__global__ void __launch_bounds__(320, (DH <= 16) ? 2 : 1) la_bwd_kernel(const LaArgs p) {
   constexpr int LDM = DH + 4;
   extern __shared__ __align__(16) float smem[];
   const LaSmem L = la_layout(DH, p.g.Mp, p.g.ldp, blockDim.x, TT, true, p.rot == ERV_ROT_CIRCULANT);

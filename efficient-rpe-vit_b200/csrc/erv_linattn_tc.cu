@@ -99,21 +99,28 @@ __device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const f
   }
 }
 
-// split an fp32 value into two bf16 (hi + lo carries ~17 significant bits)
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// ---- bf16 hi/lo splitting without conversion instructions (the XU pipe is busy with ex2) --------------------
+// hi = upper 16 bits of the fp32 pattern (truncation), lo = upper 16 bits of (v - hi); hi + lo carries >= 16
+// significant bits.  Two values are packed per 32-bit word with one byte-permute each.
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
+  hi = __byte_perm(ua, ub, 0x7632);
+  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
 }
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-// 8 consecutive values -> one 16-byte chunk in each of the hi / lo bf16 images
 __device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, uint32_t off, const float (&v)[8]) {
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  uint4 h, l;
+  split_pack2(v[0], v[1], h.x, l.x);
+  split_pack2(v[2], v[3], h.y, l.y);
+  split_pack2(v[4], v[5], h.z, l.z);
+  split_pack2(v[6], v[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(img_hi + off) = h;
+  *reinterpret_cast<uint4*>(img_lo + off) = l;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // Shared-memory images (bytes).  bf16 images use 16-byte chunks of 8 elements along the fast index f (or d) and 128
@@ -121,32 +128,32 @@ __device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, u
 // Read as an MN-major operand (rows f, K = t): SBO = CH, LBO = 128; as a K-major operand (rows t, K = f): SBO = 128,
 // LBO = CH.  The same image therefore feeds phi^T [v|1] and phi [S|z].
 constexpr uint32_t kTokCh = 16 * 128;  // chunk stride of images with 128 token rows
+constexpr int kTcThreads = 512;        // 4 threads per token row, each owns a quarter of the features
 
 template <typename T, int DH>
-__global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
+__global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs p) {
   using C = TcCfg<DH>;
   constexpr int ND = C::ND;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;  // G1 completions / G2-G4 completions
   __shared__ uint32_t tmem_base_s;
   __shared__ float n2_s[128];
-  __shared__ float mx_s[2][128];
+  __shared__ float mx_s[4][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
-  const int Mp16 = p.Mp16, M = p.M, N = p.N;
-  const int FH = Mp16 / 2;            // features per thread of a row pair
-  const int nrb = (Mp16 + 127) / 128; // 128-feature row blocks of S
-  const uint32_t wbytes = tc_w_bytes(DH, Mp16);
-  // the G2 A operand always spans whole 128-feature row blocks, so the images are padded to nrb * 128 rows
-  const uint32_t phibytes = (uint32_t)nrb * 16 * kTokCh;
-  const uint32_t s_ch = (uint32_t)(Mp16 / 8) * 128;   // chunk stride of the [S|z] image (rows = features)
+  const int Mp = p.Mp16, M = p.M, N = p.N;  // Mp: features padded to a multiple of 32
+  const int FQ = Mp / 4;                     // features per thread (multiple of 8, <= 64)
+  const int nrb = (Mp + 127) / 128;          // 128-feature row blocks of S
+  const uint32_t wbytes = tc_w_bytes(DH, Mp);
+  const uint32_t phibytes = (uint32_t)nrb * 16 * kTokCh;  // padded to whole row blocks (G2 reads 128 rows per block)
+  const uint32_t s_ch = (uint32_t)(Mp / 8) * 128;         // chunk stride of the [S|z] image (rows = features)
   uint8_t* wh = smem;
   uint8_t* wl = wh + wbytes;
   uint8_t* xh = wl + wbytes;
   uint8_t* xl = xh + C::X_BYTES;
   uint8_t* phi1 = xl + C::X_BYTES;
   uint8_t* phi2 = phi1 + phibytes;
-  uint8_t* vreg = phi2 + phibytes;                     // K pass: [2 buffers][hi, lo] of (ND/8)*kTokCh; Q pass: [S|z] hi, lo
+  uint8_t* vreg = phi2 + phibytes;  // K pass: [2 buffers][hi, lo] of (ND/8)*kTokCh; Q pass: [S|z] hi, lo
   const uint32_t vbytes = (uint32_t)(ND / 8) * kTokCh;
   uint8_t* s1 = vreg;
   uint8_t* s2 = vreg + (uint32_t)(ND / 8) * s_ch;
@@ -168,10 +175,12 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
   const T* qkv = static_cast<const T*>(p.qkv);
   T* out = static_cast<T*>(p.out);
   const size_t tok_stride = (size_t)3 * p.H * DH;
-  const uint32_t idesc_p = make_idesc(FMT_TF32, 128, Mp16, false, false);
+  const uint32_t idesc_p = make_idesc(FMT_TF32, 128, Mp, false, false);
   const uint32_t idesc_g2 = make_idesc(FMT_BF16, 128, ND, true, true);
   const uint32_t idesc_g4 = make_idesc(FMT_BF16, 128, ND, false, true);
   const float kLog2e = 1.4426950408889634f;
+  const float log2_c = log2f(p.inv_sqrt_m);  // 1/sqrt(M) folded into the exponent
+  const int fbeg = part * FQ;
   int cur_h = -1;
 
   for (int pair = blockIdx.x; pair < p.B * p.H; pair += gridDim.x) {
@@ -179,8 +188,8 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
     if (h != cur_h) {  // stage W^T hi/lo TF32 images for this head: rows f, K = Dh
       cur_h = h;
       const float* om = p.omega + (size_t)h * DH * M;
-      for (int i = tid; i < Mp16 * DH; i += 256) {
-        const int d = i / Mp16, f = i % Mp16;
+      for (int i = tid; i < Mp * DH; i += kTcThreads) {
+        const int d = i / Mp, f = i % Mp;
         const float w = (f < M) ? __ldg(om + (size_t)d * M + f) : 0.f;
         const float hi = to_tf32(w), lo = to_tf32(w - hi);
         const uint32_t off = off_kmajor(f, d, 4, 4, C::X_LBO, C::X_SBO);
@@ -193,10 +202,11 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
     const T* vb = qkv + qkv_off(b, 0, 2, h, N, p.H, DH);
 
     auto emit_out = [&](int n0) {  // out = num / (den + eps) for the tile starting at n0 (reads TMEM: all lanes)
+      if (part != 0) return;       // warps 0-3 cover the 128 lanes (warp-uniform branch)
       float r[32];
       tmem_ld32(tm + lane_off + C::COL_O, r);
       const int n = n0 + row;
-      if (part == 0 && n < N) {
+      if (n < N) {
         const float den = r[DH] + kEps;
         T* ob = out + out_off(b, n, h, N, p.H, DH);
 #pragma unroll
@@ -211,13 +221,16 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
         const int n = n0 + row;
         const bool valid = n < N;
         const int nt = min(128, N - n0);
+        const int nt16 = (nt + 15) & ~15;                    // rows the contractions actually read
+        const bool warp_live = (row & ~31) < nt16;           // warp-uniform: this 32-row group holds read rows
         // ---- step 1: operand images of this tile
         if (part == 0) {
           float x[DH];
-          float n2 = 0.f;
+          float n2 = INFINITY;  // invalid rows: exponent -inf -> phi = 0
           if (valid) {
             load_row<T, DH>((pass == 0 ? kb : qb) + (size_t)n * tok_stride, x);
             prologue_row<DH>(x, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+            n2 = 0.f;
 #pragma unroll
             for (int a = 0; a < DH; ++a) n2 = fmaf(x[a], x[a], n2);
             n2 *= 0.5f;
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
           }
           n2_s[row] = n2;
           store_x_images<DH>(xh, xl, x, row);
-        } else if (pass == 0) {  // [v | 1] rows, double buffered across tiles
+        } else if (part == 1 && pass == 0 && warp_live) {  // [v | 1] rows, double buffered across tiles
           uint8_t* v1 = vreg + (uint32_t)(tile & 1) * 2 * vbytes;
           uint8_t* v2 = v1 + vbytes;
           float v[DH];
@@ -277,43 +290,56 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
           if (pass == 1) emit_out(n0 - 128);
         }
         fence_after_sync();
-        // ---- row max over the real features (FAVOR+), two threads per row
-        const int fbeg = part * FH;
-        const float n2 = n2_s[row];
+        // ---- this thread's quarter of the row: P -> registers (one TMEM read), max, phi, hi/lo bf16 images
+        uint32_t pr[8][8];  // fp32 bit patterns of P[row][fbeg + 8c + i]
+        if (warp_live) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c * 8 < FQ) tmem_ld8_nowait(tm + lane_off + fbeg + c * 8, pr[c]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c * 8 < FQ) tmem_wait_ld8(pr[c]);
+        }
         float mx = 0.f;
         if (p.kind == ERV_FEAT_FAVOR) {
           float m_part = -INFINITY;
-          for (int c0 = 0; c0 < FH; c0 += 8) {
-            uint32_t r[8];
-            tmem_ld8_nowait(tm + lane_off + fbeg + c0, r);
-            tmem_wait_ld8(r);
+          if (warp_live) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (fbeg + c0 + i < M) m_part = fmaxf(m_part, __uint_as_float(r[i]));
+            for (int c = 0; c < 8; ++c)
+              if (c * 8 < FQ) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (fbeg + c * 8 + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+              }
           }
           mx_s[part][row] = m_part;
           __syncthreads();
-          mx = fmaxf(mx_s[0][row], mx_s[1][row]);
+          mx = fmaxf(fmaxf(mx_s[0][row], mx_s[1][row]), fmaxf(mx_s[2][row], mx_s[3][row]));
         }
-        // ---- phi for this thread's features -> hi/lo bf16 images
-        const float shift = mx + n2;
-        for (int c0 = 0; c0 < FH; c0 += 8) {
-          uint32_t r[8];
-          tmem_ld8_nowait(tm + lane_off + fbeg + c0, r);
-          tmem_wait_ld8(r);
-          float ph_v[8];
+        if (warp_live) {
+          // phi = exp(P - mx - n2)/sqrt(M) = 2^(P*log2e - (mx + n2)*log2e + log2(1/sqrt(M)))
+          const float shift = fmaf(mx + n2_s[row], kLog2e, -log2_c);
+          const float scale = valid ? p.inv_sqrt_m : 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float pv = __uint_as_float(r[i]);
-            float v = 0.f;
-            if (valid && fbeg + c0 + i < M)
-              v = (p.kind == ERV_FEAT_FAVOR) ? exp2f(((pv - mx) - n2) * kLog2e) * p.inv_sqrt_m
-                                             : fmaxf(pv, 0.f) * p.inv_sqrt_m;
-            ph_v[i] = v;
-          }
-          store_split8(phi1, phi2, (uint32_t)((fbeg + c0) >> 3) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ph_v);
+          for (int c = 0; c < 8; ++c)
+            if (c * 8 < FQ) {
+              float ph_v[8];
+              const int f0 = fbeg + c * 8;
+              if (p.kind == ERV_FEAT_FAVOR) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ph_v[i] = ex2_approx(fmaf(__uint_as_float(pr[c][i]), kLog2e, -shift));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ph_v[i] = fmaxf(__uint_as_float(pr[c][i]), 0.f) * scale;
+              }
+              if (f0 + 8 > M) {  // padded features contribute nothing
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (f0 + i >= M) ph_v[i] = 0.f;
+              }
+              store_split8(phi1, phi2, (uint32_t)(f0 >> 3) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ph_v);
+            }
         }
-        (void)shift;
         fence_smem_to_async();
         fence_before_sync();
         __syncthreads();
@@ -322,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
           if (pass == 0) {  // G2: S[rb] (+)= phi^T [v|1], terms hi*hi + hi*lo + lo*hi
             const uint8_t* v1 = vreg + (uint32_t)(tile & 1) * 2 * vbytes;
             const uint8_t* v2 = v1 + vbytes;
-            const int ksteps = (nt + 15) / 16;
+            const int ksteps = nt16 / 16;
             for (int rb = 0; rb < nrb; ++rb) {
               bool acc = n0 > 0;
               for (int term = 0; term < 3; ++term) {
@@ -341,7 +367,7 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
             for (int term = 0; term < 3; ++term) {
               const uint8_t* a_img = (term == 2) ? phi2 : phi1;
               const uint8_t* b_img = (term == 1) ? s2 : s1;
-              for (int s = 0; s < Mp16 / 16; ++s) {
+              for (int s = 0; s < Mp / 16; ++s) {
                 mma_f16(tm + C::COL_O, make_desc(smem_u32(a_img) + (uint32_t)s * 2 * kTokCh, kTokCh, 128),
                         make_desc(smem_u32(b_img) + s * 256, 128, s_ch), idesc_g4, acc);
                 acc = true;
@@ -358,16 +384,18 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
       pending_b = false;
       fence_after_sync();
       if (pass == 0) {  // S (TMEM, lanes = features) -> [S|z] hi/lo bf16 images: byte(f, d) = (d/8)*s_ch + (f/8)*128 + (f%8)*16
-        float sv[32];
-        tmem_ld32(tm + lane_off + C::COL_S + (part < nrb ? part : 0) * ND, sv);
-        const int f = part * 128 + row;
-        if (part < nrb && f < Mp16) {
+        if (part < nrb) {  // warp-uniform
+          float sv[32];
+          tmem_ld32(tm + lane_off + C::COL_S + part * ND, sv);
+          const int f = part * 128 + row;
+          if (f < Mp) {
 #pragma unroll
-          for (int c = 0; c < ND / 8; ++c) {
-            float ch[8];
+            for (int c = 0; c < ND / 8; ++c) {
+              float ch[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
-            store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
+              for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
+              store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
+            }
           }
         }
         fence_before_sync();
@@ -383,14 +411,14 @@ __global__ void __launch_bounds__(256, 1) la_tc_fwd_kernel(const LaTcArgs p) {
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
-size_t la_tc_smem_bytes(int DH, int Mp16) {
+size_t la_tc_smem_bytes(int DH, int Mp) {
   const int ND = (DH + 1 + 15) / 16 * 16;
   const size_t x_bytes = 16 * (size_t)(DH / 4) * 128;
   size_t v_bytes = 4 * (size_t)(ND / 8) * kTokCh;               // 2 buffers x (hi, lo)
-  const size_t s_bytes = 2 * (size_t)(ND / 8) * (Mp16 / 8) * 128;  // hi, lo
+  const size_t s_bytes = 2 * (size_t)(ND / 8) * (Mp / 8) * 128;  // hi, lo
   if (s_bytes > v_bytes) v_bytes = s_bytes;
-  const size_t nrb = (Mp16 + 127) / 128;
-  return 2 * (size_t)tc_w_bytes(DH, Mp16) + 2 * x_bytes + 2 * nrb * 16 * kTokCh + v_bytes + 128;
+  const size_t nrb = (Mp + 127) / 128;
+  return 2 * (size_t)tc_w_bytes(DH, Mp) + 2 * x_bytes + 2 * nrb * 16 * kTokCh + v_bytes + 128;
 }
 
 bool la_tc_eligible(int N, int DH, int M) {
@@ -402,7 +430,7 @@ int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, 
                   const float* ta, const float* tb, int dtype, cudaStream_t st) {
   LaTcArgs a;
   a.qkv = qkv; a.out = out; a.omega = omega; a.ta = ta; a.tb = tb;
-  a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = (M + 15) / 16 * 16; a.kind = kind; a.rot = rot;
+  a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = (M + 31) / 32 * 32; a.kind = kind; a.rot = rot;
   a.prescale = (float)pow((double)DH, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
   const size_t smem = la_tc_smem_bytes(DH, a.Mp16);
@@ -412,7 +440,7 @@ int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, 
 #define TC_LAUNCH(TT, D)                                                  \
   do {                                                                    \
     ERV_CUDA(allow_smem(la_tc_fwd_kernel<TT, D>, smem));                  \
-    la_tc_fwd_kernel<TT, D><<<grid, 256, smem, st>>>(a);                  \
+    la_tc_fwd_kernel<TT, D><<<grid, kTcThreads, smem, st>>>(a);                  \
   } while (0)
   if (dtype == ERV_F32) {
     if (DH == 16) TC_LAUNCH(float, 16); else TC_LAUNCH(float, 8);

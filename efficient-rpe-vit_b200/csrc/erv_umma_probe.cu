@@ -75,9 +75,55 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict
   if (warp == 0) tmem_dealloc(tmem_base, cols);
 }
 
+// Timing probe: one thread issues `iters` back-to-back MMAs (M=128) of the given N / kind and reports the elapsed
+// SM clocks from first issue to completion.  Operands are whatever is in shared memory (zero-filled).
+__global__ void __launch_bounds__(128) umma_timing_kernel(int N, int bf16, int a_mn, int b_mn, int iters,
+                                                          long long* __restrict__ cycles) {
+  using namespace umma;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 32 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init_fence();
+  }
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(bf16 ? FMT_BF16 : FMT_TF32, 128, N, a_mn != 0, b_mn != 0);
+    const uint64_t ad = make_desc(smem_u32(smem), 128, 256);         // 128 rows: 16 groups x 256 B
+    const uint64_t bd = make_desc(smem_u32(smem) + 8192, 128, 256);  // up to 256 rows: 32 groups x 256 B
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (bf16) mma_f16(tm, ad, bd, idesc, i > 0);
+      else mma_tf32(tm, ad, bd, idesc, i > 0);
+    }
+    commit(&bar);
+    mbar_wait(&bar, 0);
+    cycles[0] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 }  // namespace erv
 
 using namespace erv;
+
+extern "C" int erv_debug_umma_timing(int N, int bf16, int a_mn_major, int b_mn_major, int iters, long long* cycles,
+                                     void* stream) {
+  ERV_CHECK_ARG(cycles && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0, "erv_debug_umma_timing: bad arguments");
+  umma_timing_kernel<<<1, 128, 32 * 1024, (cudaStream_t)stream>>>(N, bf16, a_mn_major, b_mn_major, iters, cycles);
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
 
 extern "C" int erv_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int a_mn_major,
                                    int b_mn_major, int bf16, void* stream) {

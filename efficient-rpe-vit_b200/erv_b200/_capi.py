@@ -46,6 +46,7 @@ SIGNATURES = {
     "erv_toeplitz_matmul_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_adam_step": (c_int, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _I, _F, c_int64, _P, _P]),
     "erv_debug_umma_gemm": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "erv_debug_umma_timing": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

@@ -164,6 +164,9 @@ int erv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * to pin the descriptor encodings. */
 int erv_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
                         int bf16, void* stream);
+/* SM clocks for `iters` back-to-back M=128 MMAs of width N issued by one thread (cycles: device int64). */
+int erv_debug_umma_timing(int N, int bf16, int a_mn_major, int b_mn_major, int iters, long long* cycles,
+                          void* stream);
 
 #ifdef __cplusplus
 }
