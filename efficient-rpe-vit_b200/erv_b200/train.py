@@ -11,10 +11,10 @@ The reference trains with torch.optim.Adam(lr=1e-3) on CrossEntropy (experiments
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import _capi as C
+from .parallel import FlatParams, world_size
 
 
 class Trainer:
@@ -26,27 +26,15 @@ class Trainer:
         self.weight_decay, self.decoupled = weight_decay, decoupled_weight_decay
         self.autocast_dtype = autocast_dtype
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.params = [p for p in model.parameters() if p.requires_grad]
-        dev = self.params[0].device
-        C.require_cuda(self.params[0])
-        sizes = [p.numel() for p in self.params]
-        total = sum(sizes)
-        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
-        self.gflat = torch.zeros(total, device=dev, dtype=torch.float32)
-        off = 0
-        for p, n in zip(self.params, sizes):  # parameters and their .grad become views of the flat buffers
-            self.flat[off:off + n].copy_(p.detach().reshape(-1))
-            p.data = self.flat[off:off + n].view_as(p)
-            p.grad = self.gflat[off:off + n].view_as(p)
-            off += n
+        self.world = world_size(process_group)
+        C.require_cuda(next(model.parameters()))
+        self.fp = FlatParams(model.parameters())
+        self.params, self.flat, self.gflat = self.fp.params, self.fp.flat, self.fp.grad
+        dev = self.flat.device
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
-        if self.world > 1:  # identical replicas: rank 0's parameters and buffers win
-            dist.broadcast(self.flat, src=0, group=self.group)
-            for b in model.buffers():
-                dist.broadcast(b, src=0, group=self.group)
+        self.fp.broadcast(model.buffers(), src=0, group=self.group)
         self.use_graph = use_graph
         self._graph = None
         self._static = None
@@ -61,8 +49,7 @@ class Trainer:
             logits = self.model(images)
         loss = F.cross_entropy(logits.float(), labels)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.gflat, group=self.group)
+        self.fp.allreduce_grad(self.group)
         self.step_count += 1
         C.check(C.load().erv_adam_step(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
                                        self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,

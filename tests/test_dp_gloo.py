@@ -1,0 +1,74 @@
+"""Data-parallel plumbing on CPU with gloo, world_size 2: replicas start identical, the
+all-reduced flat gradient equals the single-process full-batch gradient, batch shards tile the global batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from erv_b200.parallel import FlatParams, shard_slice
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model(seed):
+    torch.manual_seed(seed)
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.LayerNorm(5), torch.nn.Linear(5, 3))
+    m.register_buffer("omega", torch.randn(2, 4))
+    return m
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _model(seed=100 + rank)  # deliberately different replicas
+        fp = FlatParams(model.parameters())
+        fp.broadcast(model.buffers(), src=0)
+        g = torch.Generator().manual_seed(0)
+        x, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+        sl = shard_slice(8, rank, world)
+        fp.zero_grad()
+        # sum-reduction loss per shard, so the summed gradient is the full-batch sum
+        torch.nn.functional.cross_entropy(model(x[sl]), y[sl], reduction="sum").backward()
+        fp.allreduce_grad()
+        out[rank] = (fp.flat.clone(), fp.grad.clone(), model.omega.clone(), (sl.start, sl.stop))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_allreduce_matches_single_process():
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    ref = _model(seed=100)
+    fp = FlatParams(ref.parameters())
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+    torch.nn.functional.cross_entropy(ref(x), y, reduction="sum").backward()
+    assert out[0][3] == (0, 4) and out[1][3] == (4, 8)
+    for r in range(world):
+        flat, grad, omega, _ = out[r]
+        assert torch.equal(flat, fp.flat), "replicas must equal rank 0 after broadcast"
+        assert torch.equal(omega, ref.omega)
+        assert torch.allclose(grad, fp.grad, atol=1e-6)
+
+
+def test_flat_params_are_views_and_shards_validate():
+    m = _model(1)
+    fp = FlatParams(m.parameters())
+    assert fp.numel() == sum(p.numel() for p in m.parameters())
+    m[0].weight.data.fill_(2.0)
+    assert (fp.flat[:30] == 2.0).all()           # parameter storage is the flat buffer
+    m(torch.randn(4, 6)).sum().backward()
+    assert fp.grad.abs().sum() > 0               # autograd accumulated into the flat gradient
+    fp.zero_grad()
+    assert m[0].weight.grad.abs().sum() == 0
+    with pytest.raises(ValueError):
+        shard_slice(10, 0, 4)
