@@ -431,6 +431,9 @@ namespace erv {  // tensor-core path (erv_linattn_tc.cu)
 bool la_tc_eligible(int N, int DH, int M);
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
                   const float* ta, const float* tb, int dtype, cudaStream_t st);
+int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
+                   int H, int DH, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
+                   int dtype, cudaStream_t st);
 }  // namespace erv
 
 static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, void* dqkv, const float* omega, int B,
@@ -449,6 +452,12 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   cudaStream_t st = (cudaStream_t)stream;
   if (!bwd && la_tc_eligible(N, DH, M))
     return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
+  if (bwd && la_tc_eligible(N, DH, M) && getenv("ERV_DISABLE_TC_BWD") == nullptr) {
+    const int slots = la_grid(B, H) / H;
+    float* dgp = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;
+    if (dgp) ERV_CUDA(cudaMemsetAsync(dgp, 0, (size_t)H * slots * N * DH * sizeof(float), st));
+    return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
+  }
   LaArgs a;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.wt = (const float*)ws; a.ta = ta; a.tb = tb;
   a.dg_part = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;

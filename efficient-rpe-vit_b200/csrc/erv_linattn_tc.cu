@@ -10,125 +10,10 @@
 // owning threads in the no-swizzle K-major canonical layout (erv_umma.cuh).  The projection needs fp32-level
 // accuracy because it feeds exp(); rounding phi and S to TF32 is averaged over N*M terms and stays far below the
 // 1e-4 parity budget, the value rows are split hi+lo (tests/test_parity_gpu.py holds the kernel to 1e-4).
-#include <cuda_bf16.h>
-
-#include "erv_common.cuh"
-#include "erv_umma.cuh"
+#include "erv_tc_common.cuh"
 
 namespace erv {
-using namespace umma;
 
-struct LaTcArgs {
-  const void* qkv;
-  void* out;
-  const float* omega;  // [H][DH][M]
-  const float* ta;
-  const float* tb;
-  int B, N, H, M, Mp16, kind, rot;
-  float prescale, inv_sqrt_m;
-};
-
-template <int DH>
-struct TcCfg {
-  static constexpr int ND = (DH + 1 + 15) / 16 * 16;        // columns of [v|1] and [S|z], padded for the MMA N dim
-  static constexpr uint32_t X_LBO = 128, X_SBO = (DH / 4) * 128;  // x / w images: rows x Dh
-  static constexpr uint32_t T_LBO = 144, T_SBO = 32 * 144;  // images whose K index is the 128 tokens (padded chunks)
-  static constexpr uint32_t P_LBO = 128, P_SBO = 32 * 128;  // phi image [128 tokens x 128 features]
-  static constexpr uint32_t X_BYTES = 16 * X_SBO;           // 128 rows
-  static constexpr uint32_t PHI_BYTES = 16 * T_SBO;         // >= 16 * P_SBO
-  static constexpr uint32_t V_BYTES = (ND / 8) * T_SBO;     // one [ND x 128 tokens] image
-  static constexpr int COL_S = 256, COL_O = 256 + 2 * ND;   // TMEM columns
-};
-
-__host__ __device__ inline uint32_t tc_w_bytes(int DH, int Mp16) { return (uint32_t)(Mp16 / 8) * (DH / 4) * 128; }
-__host__ __device__ inline uint32_t tc_s_bytes(int ND, int Mp16) { return (uint32_t)(ND / 8) * (Mp16 / 4) * 144; }
-
-template <typename T, int DH>
-__device__ __forceinline__ void load_row(const T* __restrict__ p, float (&x)[DH]) {
-#pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    float4 v = ld4(p + 4 * c);
-    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-  }
-}
-
-// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
-template <int DH>
-__device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const float* __restrict__ ta,
-                                             const float* __restrict__ tb, int h, int n, int N, float prescale) {
-  if (rot == ERV_ROT_ROPE) {
-#pragma unroll
-    for (int m = 0; m < DH / 2; ++m) {
-      const float c = __ldg(ta + (size_t)n * (DH / 2) + m), s = __ldg(tb + (size_t)n * (DH / 2) + m);
-      const float xe = x[2 * m], xo = x[2 * m + 1];
-      x[2 * m] = xe * c - xo * s;
-      x[2 * m + 1] = xe * s + xo * c;
-    }
-  } else if (rot == ERV_ROT_CIRCULANT) {
-    float g[DH], y[DH];
-    load_row<float, DH>(ta + ((size_t)h * N + n) * DH, g);
-#pragma unroll
-    for (int a = 0; a < DH; ++a) {
-      float acc = 0.f;
-#pragma unroll
-      for (int b = 0; b < DH; ++b) acc = fmaf(g[(a - b) & (DH - 1)], x[b], acc);
-      y[a] = acc;
-    }
-#pragma unroll
-    for (int a = 0; a < DH; ++a) x[a] = y[a];
-  }
-#pragma unroll
-  for (int a = 0; a < DH; ++a) x[a] *= prescale;
-}
-
-// write one token row as the hi / lo TF32 images of a K-major [128 x DH] operand
-template <int DH>
-__device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const float (&x)[DH], int t) {
-  using C = TcCfg<DH>;
-#pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    float hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      hi[e] = to_tf32(x[4 * c + e]);
-      lo[e] = to_tf32(x[4 * c + e] - hi[e]);
-    }
-    const uint32_t off = (uint32_t)(t >> 3) * C::X_SBO + c * C::X_LBO + (t & 7) * 16;
-    st4(reinterpret_cast<float*>(xh + off), make_float4(hi[0], hi[1], hi[2], hi[3]));
-    st4(reinterpret_cast<float*>(xl + off), make_float4(lo[0], lo[1], lo[2], lo[3]));
-  }
-}
-
-// ---- bf16 hi/lo splitting without conversion instructions (the XU pipe is busy with ex2) --------------------
-// hi = upper 16 bits of the fp32 pattern (truncation), lo = upper 16 bits of (v - hi); hi + lo carries >= 16
-// significant bits.  Two values are packed per 32-bit word with one byte-permute each.
-__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-  const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
-  hi = __byte_perm(ua, ub, 0x7632);
-  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
-}
-__device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, uint32_t off, const float (&v)[8]) {
-  uint4 h, l;
-  split_pack2(v[0], v[1], h.x, l.x);
-  split_pack2(v[2], v[3], h.y, l.y);
-  split_pack2(v[4], v[5], h.z, l.z);
-  split_pack2(v[6], v[7], h.w, l.w);
-  *reinterpret_cast<uint4*>(img_hi + off) = h;
-  *reinterpret_cast<uint4*>(img_lo + off) = l;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Shared-memory images (bytes).  bf16 images use 16-byte chunks of 8 elements along the fast index f (or d) and 128
-// contiguous bytes per group of 8 tokens:  byte(t, f) = (f/8)*CH + (t/8)*128 + (t%8)*16 + (f%8)*2.
-// Read as an MN-major operand (rows f, K = t): SBO = CH, LBO = 128; as a K-major operand (rows t, K = f): SBO = 128,
-// LBO = CH.  The same image therefore feeds phi^T [v|1] and phi [S|z].
-constexpr uint32_t kTokCh = 16 * 128;  // chunk stride of images with 128 token rows
-constexpr int kTcThreads = 512;        // 4 threads per token row, each owns a quarter of the features
 
 template <typename T, int DH>
 __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs p) {
