@@ -15,7 +15,8 @@
 namespace erv {
 
 
-template <typename T, int DH>
+// NC = 8-feature chunks per thread: Mp = 32 * NC is compile time so the P registers are statically indexed.
+template <typename T, int DH, int NC>
 __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs p) {
   using C = TcCfg<DH>;
   constexpr int ND = C::ND;
@@ -26,9 +27,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
   __shared__ float mx_s[4][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
-  const int Mp = p.Mp16, M = p.M, N = p.N;  // Mp: features padded to a multiple of 32
-  const int FQ = Mp / 4;                     // features per thread (multiple of 8, <= 64)
-  const int nrb = (Mp + 127) / 128;          // 128-feature row blocks of S
+  constexpr int Mp = 32 * NC, FQ = 8 * NC;   // padded features; features per thread
+  constexpr int nrb = (Mp + 127) / 128;      // 128-feature row blocks of S
+  const int M = p.M, N = p.N;
   const uint32_t wbytes = tc_w_bytes(DH, Mp);
   const uint32_t phibytes = (uint32_t)nrb * 16 * kTokCh;  // padded to whole row blocks (G2 reads 128 rows per block)
   const uint32_t s_ch = (uint32_t)(Mp / 8) * 128;         // chunk stride of the [S|z] image (rows = features)
@@ -176,22 +177,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
         }
         fence_after_sync();
         // ---- this thread's quarter of the row: P -> registers (one TMEM read), max, phi, hi/lo bf16 images
-        uint32_t pr[8][8];  // fp32 bit patterns of P[row][fbeg + 8c + i]
+        uint32_t pr[NC][8];  // fp32 bit patterns of P[row][fbeg + 8c + i]
         if (warp_live) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c * 8 < FQ) tmem_ld8_nowait(tm + lane_off + fbeg + c * 8, pr[c]);
+          for (int c = 0; c < NC; ++c)
+            tmem_ld8_nowait(tm + lane_off + fbeg + c * 8, pr[c]);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c * 8 < FQ) tmem_wait_ld8(pr[c]);
+          for (int c = 0; c < NC; ++c)
+            tmem_wait_ld8(pr[c]);
         }
         float mx = 0.f;
         if (p.kind == ERV_FEAT_FAVOR) {
           float m_part = -INFINITY;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c * 8 < FQ) {
+            for (int c = 0; c < NC; ++c)
+              {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                   if (fbeg + c * 8 + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
           const float shift = fmaf(mx + n2_s[row], kLog2e, -log2_c);
           const float scale = valid ? p.inv_sqrt_m : 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c * 8 < FQ) {
+          for (int c = 0; c < NC; ++c)
+            {
               float ph_v[8];
               const int f0 = fbeg + c * 8;
               if (p.kind == ERV_FEAT_FAVOR) {
@@ -308,29 +309,29 @@ size_t la_tc_smem_bytes(int DH, int Mp) {
 
 bool la_tc_eligible(int N, int DH, int M) {
   static const bool disabled = getenv("ERV_DISABLE_TC") != nullptr;
-  return !disabled && (DH == 8 || DH == 16) && M <= 256 && N >= 33;
+  return !disabled && DH == 16 && M <= 256 && N >= 33;
 }
 
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
                   const float* ta, const float* tb, int dtype, cudaStream_t st) {
   LaTcArgs a;
   a.qkv = qkv; a.out = out; a.omega = omega; a.ta = ta; a.tb = tb;
-  a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = (M + 31) / 32 * 32; a.kind = kind; a.rot = rot;
+  a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = M <= 64 ? 64 : (M <= 128 ? 128 : 256); a.kind = kind; a.rot = rot;
   a.prescale = (float)pow((double)DH, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
   const size_t smem = la_tc_smem_bytes(DH, a.Mp16);
   int grid = (kNumSMs / H) * H;  // multiple of H: each CTA stays on one head (W images staged once)
   if (grid < H) grid = H;
   if (grid > B * H) grid = B * H;
-#define TC_LAUNCH(TT, D)                                                  \
-  do {                                                                    \
-    ERV_CUDA(allow_smem(la_tc_fwd_kernel<TT, D>, smem));                  \
-    la_tc_fwd_kernel<TT, D><<<grid, kTcThreads, smem, st>>>(a);                  \
+#define TC_LAUNCH(TT, NC_)                                                      \
+  do {                                                                          \
+    ERV_CUDA(allow_smem(la_tc_fwd_kernel<TT, 16, NC_>, smem));                  \
+    la_tc_fwd_kernel<TT, 16, NC_><<<grid, kTcThreads, smem, st>>>(a);           \
   } while (0)
   if (dtype == ERV_F32) {
-    if (DH == 16) TC_LAUNCH(float, 16); else TC_LAUNCH(float, 8);
+    if (a.Mp16 == 64) TC_LAUNCH(float, 2); else if (a.Mp16 == 128) TC_LAUNCH(float, 4); else TC_LAUNCH(float, 8);
   } else {
-    if (DH == 16) TC_LAUNCH(__nv_bfloat16, 16); else TC_LAUNCH(__nv_bfloat16, 8);
+    if (a.Mp16 == 64) TC_LAUNCH(__nv_bfloat16, 2); else if (a.Mp16 == 128) TC_LAUNCH(__nv_bfloat16, 4); else TC_LAUNCH(__nv_bfloat16, 8);
   }
 #undef TC_LAUNCH
   ERV_LAUNCH_CHECK();

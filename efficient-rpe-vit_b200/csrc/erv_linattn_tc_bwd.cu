@@ -40,7 +40,9 @@ __device__ __forceinline__ void unpack8(const uint8_t* hi_img, const uint8_t* lo
   }
 }
 
-template <typename T, int DH>
+// NRB feature halves (row blocks of S), CPH 8-feature chunks per thread and half: Mp = NRB * CPH * 32 is compile time
+// so the per-thread feature registers are statically indexed.
+template <typename T, int DH, int NRB, int CPH>
 __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdArgs p) {
   using C = TcCfg<DH>;
   constexpr int ND = C::ND, RW = DH + 4;
@@ -53,11 +55,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
   __shared__ float z_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
-  const int Mp = p.Mp, M = p.M, N = p.N;
-  const int nrb = (Mp + 127) / 128;  // feature halves (row blocks of S)
-  const int HF = Mp / nrb;           // features per half (multiple of 32)
-  const int FPH = HF / 4;            // features per thread and half (multiple of 8, <= 32)
-  const int CPH = FPH / 8;           // 8-feature chunks per thread and half (<= 4)
+  constexpr int nrb = NRB, HF = CPH * 32, FPH = CPH * 8, Mp = NRB * HF, NC = NRB * CPH;
+  const int M = p.M, N = p.N;
   const uint32_t wbytes = tc_w_bytes(DH, Mp);
   const uint32_t s_ch = (uint32_t)(Mp / 8) * 128;
   const uint32_t avbytes = (uint32_t)(ND / 8) * kTokCh;
@@ -72,10 +71,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
   uint8_t* av2 = av1 + avbytes;
   uint8_t* s1 = av2 + avbytes;              // [S|z] then [dS|dz]: byte(f, j) = (j/8)*s_ch + (f/8)*128 + (f%8)*16 + (j%8)*2
   uint8_t* s2 = s1 + (uint32_t)(ND / 8) * s_ch;
+  float* w32 = reinterpret_cast<float*>(s2 + (uint32_t)(ND / 8) * s_ch);  // [Mp][RW] fp32: W^T rows, column DH = 1 (rowsum)
+  float* ds32 = w32 + Mp * RW;                                            // [Mp][RW] fp32: dS rows (written after the Q sweep)
 
-  // chunk c of this thread: half c>>2, local chunk c&3
-  auto chunk_live = [&](int c) { return (c & 3) < CPH && (c >> 2) < nrb; };
-  auto feat0 = [&](int c) { return (c >> 2) * HF + part * FPH + (c & 3) * 8; };
+  // chunk c of this thread: half c / CPH, local chunk c % CPH
+  auto feat0 = [&](int c) { return (c / CPH) * HF + part * FPH + (c % CPH) * 8; };
 
   for (int i = tid; i < (int)(2 * avbytes / 16); i += kTcThreads)  // columns DH+1.. of the a/[v|1] images stay zero
     reinterpret_cast<uint4*>(av1)[i] = make_uint4(0, 0, 0, 0);
@@ -117,6 +117,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         const uint32_t off = off_kmajor(f, d, 4, 4, C::X_LBO, C::X_SBO);
         *reinterpret_cast<float*>(wh + off) = hi;
         *reinterpret_cast<float*>(wl + off) = lo;
+        w32[f * RW + d] = w;
+      }
+      for (int i = tid; i < Mp * 4; i += kTcThreads) {
+        const int f = i >> 2, j = DH + (i & 3);
+        w32[f * RW + j] = (j == DH && f < M) ? 1.f : 0.f;
       }
     }
     float* dg_slot = (p.rot == ERV_ROT_CIRCULANT && p.dg_part)
@@ -134,36 +139,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         const int nt16 = (min(128, N - n0) + 15) & ~15;
         const bool warp_live = (row & ~31) < nt16;
         // ---- step 1: operand images; part 0 keeps the prepared row, part 1 the value / gradient row
-        float xs[DH];   // part 0: prepared q or k row
-        float aux[DH];  // part 1: v (K passes) or dO (Q pass)
+        float rowv[DH];  // part 0: prepared q or k row; part 1: v (K passes) or dO (Q pass)
         float dot = 0.f;
         if (part == 0) {
           float n2 = INFINITY;
           if (valid) {
-            load_row<T, DH>(xb + (size_t)n * tok_stride, xs);
-            prologue_row<DH>(xs, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+            load_row<T, DH>(xb + (size_t)n * tok_stride, rowv);
+            prologue_row<DH>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
             n2 = 0.f;
 #pragma unroll
-            for (int a = 0; a < DH; ++a) n2 = fmaf(xs[a], xs[a], n2);
+            for (int a = 0; a < DH; ++a) n2 = fmaf(rowv[a], rowv[a], n2);
             n2 *= 0.5f;
           } else {
 #pragma unroll
-            for (int a = 0; a < DH; ++a) xs[a] = 0.f;
+            for (int a = 0; a < DH; ++a) rowv[a] = 0.f;
           }
           n2_s[row] = n2;
-          store_x_images<DH>(xh, xl, xs, row);
+          store_x_images<DH>(xh, xl, rowv, row);
         } else if (part == 1) {
 #pragma unroll
-          for (int d = 0; d < DH; ++d) aux[d] = 0.f;
+          for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
           if (valid) {
             if (pass == 1) {
               float o[DH];
-              load_row<T, DH>(dout + out_off(b, n, h, N, p.H, DH), aux);
+              load_row<T, DH>(dout + out_off(b, n, h, N, p.H, DH), rowv);
               load_row<T, DH>(outp + out_off(b, n, h, N, p.H, DH), o);
 #pragma unroll
-              for (int d = 0; d < DH; ++d) dot = fmaf(aux[d], o[d], dot);
+              for (int d = 0; d < DH; ++d) dot = fmaf(rowv[d], o[d], dot);
             } else {
-              load_row<T, DH>(vb + (size_t)n * tok_stride, aux);
+              load_row<T, DH>(vb + (size_t)n * tok_stride, rowv);
             }
           }
           if (pass != 1 && warp_live) {  // [v | 1] image
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             for (int c = 0; c < DH / 8; ++c) {
               float ch[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) ch[e] = aux[8 * c + e];
+              for (int e = 0; e < 8; ++e) ch[e] = rowv[8 * c + e];
               store_split8(av1, av2, c * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ch);
             }
             const float ones[8] = {valid ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -202,22 +206,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         ph_a ^= 1;
         fence_after_sync();
         // ---- P -> registers, row max, phi (kept in pr as fp32 bit patterns)
-        uint32_t pr[8][8];
+        uint32_t pr[NC][8];
         if (warp_live) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (chunk_live(c)) tmem_ld8_nowait(tm + lane_off + COL_P + feat0(c), pr[c]);
+          for (int c = 0; c < NC; ++c)
+            tmem_ld8_nowait(tm + lane_off + COL_P + feat0(c), pr[c]);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (chunk_live(c)) tmem_wait_ld8(pr[c]);
+          for (int c = 0; c < NC; ++c)
+            tmem_wait_ld8(pr[c]);
         }
         float mx = 0.f;
         if (favor) {
           float m_part = -INFINITY;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (chunk_live(c)) {
+            for (int c = 0; c < NC; ++c)
+              {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                   if (feat0(c) + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
@@ -250,8 +254,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           const float scale = valid ? p.inv_sqrt_m : 0.f;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (chunk_live(c)) {
+            for (int c = 0; c < NC; ++c)
+              {
                 const int f0 = feat0(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
               }
           } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
               for (int i = 0; i < 8; ++i) pr[c][i] = 0u;
           }
@@ -272,12 +276,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         auto store_half = [&](int hb) {
           if (!warp_live) return;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (chunk_live(c) && (c >> 2) == hb) {
+          for (int c = 0; c < NC; ++c)
+            if (c / CPH == hb) {
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(pr[c][i]);
-              store_split8(phi1, phi2, (uint32_t)(part * CPH + (c & 3)) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, v);
+              store_split8(phi1, phi2, (uint32_t)(part * CPH + (c % CPH)) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, v);
             }
         };
         // D[COL_S + hb*ND] (+)= phi_half^T rows  (rows image = av1/av2)
@@ -324,23 +328,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           for (int j = 0; j < RW; ++j) acc[j] = 0.f;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (chunk_live(c)) {
+            for (int c = 0; c < NC; ++c)
+              {
                 const int f0 = feat0(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float g = __uint_as_float(pr[c][i]);
-                  const uint32_t off = (uint32_t)((f0 + i) >> 3) * C::X_SBO + ((f0 + i) & 7) * 16;
+                  const float* wr = w32 + (f0 + i) * RW;
 #pragma unroll
-                  for (int cd = 0; cd < DH / 4; ++cd) {
-                    const float4 a = ld4(reinterpret_cast<const float*>(wh + off + cd * C::X_LBO));
-                    const float4 bq = ld4(reinterpret_cast<const float*>(wl + off + cd * C::X_LBO));
-                    acc[4 * cd] = fmaf(g, a.x + bq.x, acc[4 * cd]);
-                    acc[4 * cd + 1] = fmaf(g, a.y + bq.y, acc[4 * cd + 1]);
-                    acc[4 * cd + 2] = fmaf(g, a.z + bq.z, acc[4 * cd + 2]);
-                    acc[4 * cd + 3] = fmaf(g, a.w + bq.w, acc[4 * cd + 3]);
+                  for (int cd = 0; cd < RW / 4; ++cd) {
+                    const float4 a = ld4(wr + 4 * cd);
+                    acc[4 * cd] = fmaf(g, a.x, acc[4 * cd]);
+                    acc[4 * cd + 1] = fmaf(g, a.y, acc[4 * cd + 1]);
+                    acc[4 * cd + 2] = fmaf(g, a.z, acc[4 * cd + 2]);
+                    acc[4 * cd + 3] = fmaf(g, a.w, acc[4 * cd + 3]);
                   }
-                  acc[DH] += g;
                 }
               }
           }
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             float dy[DH];
 #pragma unroll
             for (int d = 0; d < DH; ++d)
-              dy[d] = (favor ? acc[d] - xs[d] * acc[DH] : acc[d]) * p.prescale;
+              dy[d] = (favor ? acc[d] - rowv[d] * acc[DH] : acc[d]) * p.prescale;
             float dxr[DH];
             if (p.rot == ERV_ROT_ROPE) {
 #pragma unroll
@@ -392,8 +394,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         auto load_dphi_to_g = [&]() {
           if (!warp_live) return;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (chunk_live(c)) {
+          for (int c = 0; c < NC; ++c)
+            {
               uint32_t r[8];
               tmem_ld8_nowait(tm + lane_off + COL_P + feat0(c), r);
               tmem_wait_ld8(r);
@@ -421,8 +423,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           float den_part = 0.f;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (chunk_live(c)) {
+            for (int c = 0; c < NC; ++c)
+              {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) den_part = fmaf(__uint_as_float(pr[c][i]), z_s[feat0(c) + i], den_part);
               }
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             for (int c = 0; c < DH / 8; ++c) {
               float ch[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) ch[e] = aux[8 * c + e] * r;
+              for (int e = 0; e < 8; ++e) ch[e] = rowv[8 * c + e] * r;
               store_split8(av1, av2, c * kTokCh + (row >> 3) * 128 + (row & 7) * 16, ch);
             }
             const float dd[8] = {-dot * r, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -475,19 +477,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           for (int j = 0; j < RW; ++j) acc[j] = 0.f;
           if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (chunk_live(c)) {
+            for (int c = 0; c < NC; ++c)
+              {
                 const int f0 = feat0(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float ph_v = __uint_as_float(pr[c][i]);
-                  const uint32_t off = (uint32_t)((f0 + i) >> 3) * 128 + ((f0 + i) & 7) * 16;
+                  const float* dr = ds32 + (f0 + i) * RW;
 #pragma unroll
-                  for (int cj = 0; cj < DH / 8; ++cj) {
-                    float ds[8];
-                    unpack8(s1, s2, cj * s_ch + off, ds);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[8 * cj + e] = fmaf(ph_v, ds[e], acc[8 * cj + e]);
+                  for (int cd = 0; cd < DH / 4; ++cd) {
+                    const float4 a = ld4(dr + 4 * cd);
+                    acc[4 * cd] = fmaf(ph_v, a.x, acc[4 * cd]);
+                    acc[4 * cd + 1] = fmaf(ph_v, a.y, acc[4 * cd + 1]);
+                    acc[4 * cd + 2] = fmaf(ph_v, a.z, acc[4 * cd + 2]);
+                    acc[4 * cd + 3] = fmaf(ph_v, a.w, acc[4 * cd + 3]);
                   }
                 }
               }
@@ -522,7 +525,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
               for (int e = 0; e < 8; ++e) ch[e] = (8 * c + e <= DH) ? sv[8 * c + e] : 0.f;
               store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
             }
-            if (pass == 0) z_s[f] = sv[DH];
+            if (pass == 0) {
+              z_s[f] = sv[DH];
+            } else {
+#pragma unroll
+              for (int j = 0; j < DH; j += 4) st4(ds32 + f * RW + j, make_float4(sv[j], sv[j + 1], sv[j + 2], sv[j + 3]));
+            }
           }
         }
         fence_smem_to_async();
@@ -536,14 +544,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
-static int tc_bwd_mp(int M) { return M <= 128 ? (M + 31) / 32 * 32 : (M + 63) / 64 * 64; }
+static int tc_bwd_mp(int M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
 
 size_t la_tc_bwd_smem_bytes(int DH, int M) {
   const int Mp = tc_bwd_mp(M);
   const int ND = (DH + 1 + 15) / 16 * 16;
   const size_t x_bytes = 16 * (size_t)(DH / 4) * 128;
   return 2 * (size_t)tc_w_bytes(DH, Mp) + 2 * x_bytes + 2 * 16 * (size_t)kTokCh + 2 * (size_t)(ND / 8) * kTokCh +
-         2 * (size_t)(ND / 8) * (Mp / 8) * 128 + 128;
+         2 * (size_t)(ND / 8) * (Mp / 8) * 128 + 2 * (size_t)Mp * (DH + 4) * sizeof(float) + 128;
 }
 
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
@@ -559,15 +567,16 @@ int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqk
   if (grid < H) grid = H;
   if (grid > B * H) grid = B * H;
   if (grid / H > slots && dg_part != nullptr) grid = slots * H;  // never more CTAs per head than gradient slots
-#define TCB_LAUNCH(TT, D)                                                  \
-  do {                                                                     \
-    ERV_CUDA(allow_smem(la_tc_bwd_kernel<TT, D>, smem));                   \
-    la_tc_bwd_kernel<TT, D><<<grid, kTcThreads, smem, st>>>(a);            \
+#define TCB_LAUNCH(TT, NRB_, CPH_)                                                  \
+  do {                                                                              \
+    ERV_CUDA(allow_smem(la_tc_bwd_kernel<TT, 16, NRB_, CPH_>, smem));               \
+    la_tc_bwd_kernel<TT, 16, NRB_, CPH_><<<grid, kTcThreads, smem, st>>>(a);        \
   } while (0)
+  if (DH != 16) { set_error("tensor-core backward: head_dim %d not instantiated", DH); return ERV_E_UNSUPPORTED; }
   if (dtype == ERV_F32) {
-    if (DH == 16) TCB_LAUNCH(float, 16); else TCB_LAUNCH(float, 8);
+    if (a.Mp == 64) TCB_LAUNCH(float, 1, 2); else if (a.Mp == 128) TCB_LAUNCH(float, 1, 4); else TCB_LAUNCH(float, 2, 4);
   } else {
-    if (DH == 16) TCB_LAUNCH(__nv_bfloat16, 16); else TCB_LAUNCH(__nv_bfloat16, 8);
+    if (a.Mp == 64) TCB_LAUNCH(__nv_bfloat16, 1, 2); else if (a.Mp == 128) TCB_LAUNCH(__nv_bfloat16, 1, 4); else TCB_LAUNCH(__nv_bfloat16, 2, 4);
   }
 #undef TCB_LAUNCH
   ERV_LAUNCH_CHECK();
