@@ -45,6 +45,12 @@ SIGNATURES = {
     "erv_toeplitz_matmul_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_toeplitz_matmul_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_adam_step": (c_int, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _I, _F, c_int64, _P, _P]),
+    "erv_linear_wgrad_supported": (c_int, [_I, _I, _I]),
+    "erv_linear_wgrad_workspace": (c_size_t, [_I, _I, _I]),
+    "erv_linear_wgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "erv_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "erv_layernorm_bwd_workspace": (c_size_t, [_I, _I]),
+    "erv_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
     "erv_debug_umma_gemm": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "erv_debug_umma_timing": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
 }

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..nn import Linear
 from ..rpe import KERPLEPositionalEncoding
 from ._rotation import rotation_args
 from .base import BaseAttention
@@ -28,8 +29,8 @@ class RandomFeatureAttention(BaseAttention):
         self.num_features = num_features
         self.use_orthogonal = use_orthogonal
         self.feature_redraw_interval = feature_redraw_interval
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = Linear(dim, dim)
         self.proj_dropout = nn.Dropout(dropout)
         self.register_buffer("omega", self._draw_features())
         self.register_buffer("redraw_counter", torch.tensor(0))

@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..nn import Linear
 from ..rpe import KERPLEPositionalEncoding
 from ._rotation import rotation_args
 from .base import BaseAttention
@@ -13,8 +14,8 @@ from .base import BaseAttention
 class SoftmaxAttention(BaseAttention):
     def __init__(self, dim: int, heads: int, dropout: float = 0.0, qkv_bias: bool = False):
         super().__init__(dim, heads, dropout)
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = Linear(dim, dim)
         self.attn_dropout = nn.Dropout(dropout)  # kept for module-tree parity; the kernel applies it
         self.proj_dropout = nn.Dropout(dropout)
 

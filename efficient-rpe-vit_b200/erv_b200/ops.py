@@ -356,3 +356,88 @@ class _Toeplitz(torch.autograd.Function):
 
 def toeplitz_matmul(c, x):
     return _Toeplitz.apply(c, x)
+
+
+# ---- the rest of the block: Linear weight/bias gradient, LayerNorm -------------------------------
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b.  Forward and dx stay library GEMMs; dW/db use the token-split kernel when the shape fits it."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        o, i = weight.shape
+        dy2 = dy.reshape(-1, o)
+        x2 = x.reshape(-1, i)
+        if x2.dtype != dy2.dtype:
+            x2 = x2.to(dy2.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight.to(dy2.dtype)).reshape(x.shape).to(x.dtype)
+        r = dy2.shape[0]
+        lib = C.load() if dy2.is_cuda else None
+        if (lib is not None and dy2.dtype in (torch.float32, torch.bfloat16) and weight.dtype == torch.float32
+                and lib.erv_linear_wgrad_supported(r, o, i)):
+            dy2, x2 = dy2.contiguous(), x2.contiguous()
+            dw = torch.empty_like(weight)
+            db = torch.empty(o, device=weight.device, dtype=torch.float32) if ctx.has_bias else None
+            nbytes = lib.erv_linear_wgrad_workspace(r, o, i)
+            ws = C.workspace(nbytes, dy2.device)
+            C.check(lib.erv_linear_wgrad(C.ptr(dy2), C.ptr(x2), C.ptr(dw), C.ptr(db), r, o, i, C.dtype_code(dy2), C.ptr(ws),
+                                         nbytes, C.stream()), "linear_wgrad")
+        else:
+            if ctx.needs_input_grad[1]:
+                dw = (dy2.t() @ x2).to(weight.dtype)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = dy2.sum(dim=0).to(weight.dtype)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    return _Linear.apply(x, weight, bias)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        c = shape[-1]
+        x2 = x.reshape(-1, c).contiguous()
+        r = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(r, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        C.check(C.load().erv_layernorm_fwd(C.ptr(x2), C.ptr(weight), C.ptr(bias), C.ptr(y), C.ptr(mean), C.ptr(rstd), r, c,
+                                           float(eps), C.stream()), "layernorm")
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.shape = shape
+        return y.reshape(shape)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        r, c = x2.shape
+        dy2 = dy.reshape(r, c).to(torch.float32).contiguous()
+        lib = C.load()
+        dx = torch.empty_like(x2)
+        dg, db = torch.empty_like(weight), torch.empty_like(weight)
+        nbytes = lib.erv_layernorm_bwd_workspace(r, c)
+        ws = C.workspace(nbytes, x2.device)
+        C.check(lib.erv_layernorm_bwd(C.ptr(dy2), C.ptr(x2), C.ptr(weight), C.ptr(mean), C.ptr(rstd), C.ptr(dx), C.ptr(dg),
+                                      C.ptr(db), r, c, C.ptr(ws), nbytes, C.stream()), "layernorm_bwd")
+        return dx.reshape(ctx.shape), dg, db, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    if (not x.is_cuda) or x.shape[-1] > 256 or weight is None or bias is None or weight.dtype != torch.float32:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+    return _LayerNorm.apply(x, weight, bias, eps)

@@ -9,6 +9,8 @@ from typing import Callable, Dict, Optional
 import torch
 import torch.nn as nn
 
+from .nn import LayerNorm, Linear
+
 
 class UnifiedTransformerBlock(nn.Module):
     """x + attn(norm1(x), rpe) ; x + mlp(norm2(x))   (unified_transformer.py:64-90)."""
@@ -20,10 +22,10 @@ class UnifiedTransformerBlock(nn.Module):
         self.mlp_dim = mlp_dim or dim * 4
         self.attention = attention
         self.rpe = rpe
-        self.mlp = nn.Sequential(nn.Linear(dim, self.mlp_dim), nn.GELU(), nn.Dropout(dropout),
-                                 nn.Linear(self.mlp_dim, dim), nn.Dropout(dropout))
-        self.norm1 = nn.LayerNorm(dim)
-        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = nn.Sequential(Linear(dim, self.mlp_dim), nn.GELU(), nn.Dropout(dropout),
+                                 Linear(self.mlp_dim, dim), nn.Dropout(dropout))
+        self.norm1 = LayerNorm(dim)
+        self.norm2 = LayerNorm(dim)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x + self.attention(self.norm1(x), rpe=self.rpe)  # the RPE goes INTO the attention
@@ -48,7 +50,7 @@ class BaseViT(nn.Module):
         self.num_patches = (image_size // patch_size) ** 2
         self.patch_dim = in_channels * patch_size * patch_size
 
-        self.patch_embedding = nn.Linear(self.patch_dim, dim)
+        self.patch_embedding = Linear(self.patch_dim, dim)
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
         self.pos_embedding = nn.Parameter(torch.randn(1, self.num_patches + 1, dim))
         blocks = []
@@ -58,7 +60,7 @@ class BaseViT(nn.Module):
             rpe = rpe_builder(num_patches=self.num_patches + 1, dim=dim, heads=heads) if rpe_builder else None
             blocks.append(UnifiedTransformerBlock(dim, attention, rpe, mlp_dim, dropout))
         self.transformer_blocks = nn.ModuleList(blocks)
-        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+        self.mlp_head = nn.Sequential(LayerNorm(dim), Linear(dim, num_classes))
         self._init_weights()
 
     def _init_weights(self):  # base_vit.py:153-172

@@ -157,6 +157,26 @@ int erv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
                   float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
 
+/* ---- the rest of the block, for the reference's small model dims ------------- */
+
+/* Weight and bias gradient of a Linear layer (base_vit.py:85, unified_transformer.py:53-59, favor_plus.py:59-62):
+ * dw[O, I] = sum_r dy[r, O] x[r, I], db[O] = sum_r dy[r, O] (db may be NULL), reduction split over the R token rows.
+ * dy, x: fp32 or bf16 (dtype), contiguous; dw, db: fp32.  erv_linear_wgrad_supported() tells whether the shape is
+ * handled (small O*I, many rows); other shapes belong to the library GEMM. */
+int erv_linear_wgrad_supported(int R, int O, int I);
+size_t erv_linear_wgrad_workspace(int R, int O, int I);
+int erv_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int R, int O, int I, int dtype,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* LayerNorm over the last dimension C of x [R, C] fp32 (unified_transformer.py:61-62, base_vit.py:105), biased variance,
+ * one warp per row.  mean / rstd [R] are saved for the backward. */
+int erv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                      int R, int C, float eps, void* stream);
+size_t erv_layernorm_bwd_workspace(int R, int C);
+int erv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      float* dx, float* dgamma, float* dbeta, int R, int C, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- diagnostics -------------------------------------------------------------------------- */
 
 /* D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (TF32 or BF16 operands, fp32 accumulate in TMEM) using the shared-
