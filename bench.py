@@ -218,13 +218,13 @@ def main():
 
     # ---- roofline: dominant attention kernel, CUDA events around its launches (separate eager pass) --------
     roofline = None
+    ops.PROFILE = {}
+    for i in range(6):  # every rank runs the pass (the step contains the gradient all-reduce)
+        trainer._step_impl(*pool[i % pool_n])
+    torch.cuda.synchronize()
+    stats = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.PROFILE.items()}
+    ops.PROFILE = None
     if rank == 0:
-        ops.PROFILE = {}
-        for i in range(6):
-            trainer._step_impl(*pool[i % pool_n])
-        torch.cuda.synchronize()
-        stats = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.PROFILE.items()}
-        ops.PROFILE = None
         n_tok = (w["image"] // w["patch"]) ** 2 + 1
         esize = 2 if autocast is not None else 4
         per_call = {k: statistics.mean(v[len(v) // 3:]) for k, v in stats.items() if v}  # drop the first third (warm-up)
@@ -267,7 +267,14 @@ def main():
         line["config"]["tokens"] = (w["image"] // w["patch"]) ** 2 + 1
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graph holds NCCL work; drop it before tearing the communicator down, and do not let a slow
+        # communicator abort keep the rank alive after the result line has been printed.
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+        trainer._graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -65,15 +65,26 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const T* __restrict_
   if ((int)threadIdx.x < O) dst[O * I + threadIdx.x] = bsum;
 }
 
-// out[i] = sum_g part[g][i]; the first n_w entries go to dw, the rest to db (if non-null)
-__global__ void partial_sum_kernel(const float* __restrict__ part, int G, int stride, float* __restrict__ dw, int n_w,
-                                   float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= stride) return;
+// out[i] = sum_g part[g][i]; the first n_w entries go to dw, the rest to db (if non-null).
+// Block = 32 outputs x 8 partial slices: each thread sums every 8th partial (coalesced over i), then the 8 slices are
+// combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int G, int stride,
+                                                          float* __restrict__ dw, int n_w, float* __restrict__ db) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int g = 0; g < G; ++g) acc += part[(size_t)g * stride + i];
-  if (i < n_w) dw[i] = acc;
-  else if (db != nullptr) db[i - n_w] = acc;
+  if (i < stride)
+    for (int g = slice; g < G; g += 8) acc += part[(size_t)g * stride + i];
+  red[slice][lane] = acc;
+  __syncthreads();
+  if (slice == 0 && i < stride) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    if (i < n_w) dw[i] = t;
+    else if (db != nullptr) db[i - n_w] = t;
+  }
 }
 
 // ---- LayerNorm: one warp per row, lane owns columns lane, lane+32, ... (C <= 32*LN_MAX) -----------------------------
@@ -190,8 +201,8 @@ static int ln_grid(int R) {
 using namespace erv;
 
 static int wgrad_slabs(int R) {
-  int g = (R + WG_KC - 1) / WG_KC;
-  return g < 2 * kNumSMs ? (g < 1 ? 1 : g) : 2 * kNumSMs;
+  int g = (R + 2 * WG_KC - 1) / (2 * WG_KC);  // at least two chunks per slab
+  return g < 4 * kNumSMs ? (g < 1 ? 1 : g) : 4 * kNumSMs;
 }
 
 extern "C" int erv_linear_wgrad_supported(int R, int O, int I) {
@@ -226,7 +237,7 @@ extern "C" int erv_linear_wgrad(const void* dy, const void* x, float* dw, float*
                                                                   R, O, I, rows_per_cta);
   ERV_LAUNCH_CHECK();
   const int stride = O * I + O;
-  partial_sum_kernel<<<(stride + 255) / 256, 256, 0, st>>>(part, G, stride, dw, O * I, db);
+  partial_sum_kernel<<<(stride + 31) / 32, 256, 0, st>>>(part, G, stride, dw, O * I, db);
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }
@@ -261,7 +272,7 @@ extern "C" int erv_layernorm_bwd(const float* dy, const float* x, const float* g
 #undef LN_BWD
   ERV_LAUNCH_CHECK();
   // dgamma = first C entries, dbeta = next C
-  partial_sum_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(part, grid, 2 * C, dgamma, C, dbeta);
+  partial_sum_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, grid, 2 * C, dgamma, C, dbeta);
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }

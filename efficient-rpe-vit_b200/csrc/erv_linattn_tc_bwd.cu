@@ -27,7 +27,10 @@ struct LaTcBwdArgs {
   float* dg_part;  // [H][slots][N][DH], circulant only
   int B, N, H, M, Mp, kind, rot, slots;
   float prescale, inv_sqrt_m;
+  long long* trace;  // optional: CTA 0 / thread 0 stamps clock64() at phase boundaries (erv_debug_set_trace)
 };
+
+static long long* g_trace = nullptr;
 
 __device__ __forceinline__ void unpack8(const uint8_t* hi_img, const uint8_t* lo_img, uint32_t off, float (&v)[8]) {
   const uint4 h = *reinterpret_cast<const uint4*>(hi_img + off);
@@ -91,6 +94,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
   const uint32_t tm = tmem_base_s;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t ph_a = 0, ph_b = 0;
+  int tr_i = 0;
+  auto TR = [&](int tag) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && tr_i < 1000) {
+      p.trace[2 * tr_i] = tag;
+      p.trace[2 * tr_i + 1] = clock64();
+      ++tr_i;
+    }
+  };
 
   const T* qkv = static_cast<const T*>(p.qkv);
   const T* outp = static_cast<const T*>(p.out);
@@ -138,6 +149,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         const bool valid = n < N;
         const int nt16 = (min(128, N - n0) + 15) & ~15;
         const bool warp_live = (row & ~31) < nt16;
+        TR(pass * 100 + 0);
         // ---- step 1: operand images; part 0 keeps the prepared row, part 1 the value / gradient row
         float rowv[DH];  // part 0: prepared q or k row; part 1: v (K passes) or dO (Q pass)
         float dot = 0.f;
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         fence_smem_to_async();
         fence_before_sync();
         __syncthreads();
+        TR(pass * 100 + 1);
         // ---- G1: P = x W^T (3xTF32)
         if (tid == 0) {
           fence_after_sync();
@@ -205,6 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1;
         fence_after_sync();
+        TR(pass * 100 + 2);
         // ---- P -> registers, row max, phi (kept in pr as fp32 bit patterns)
         uint32_t pr[NC][8];
         if (warp_live) {
@@ -272,6 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
               for (int i = 0; i < 8; ++i) pr[c][i] = 0u;
           }
         }
+        TR(pass * 100 + 3);
         // stores one feature half of the values held in pr into the phi images
         auto store_half = [&](int hb) {
           if (!warp_live) return;
@@ -417,6 +432,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             mbar_wait(&bar_b, ph_b);
             ph_b ^= 1;
             fence_after_sync();
+            TR(4 + hb);
           }
         } else if (pass == 1) {
           // ---- Q: den, a, dS += phi_q^T a, dphi_q = a [S|z]^T
@@ -444,6 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             const float dd[8] = {-dot * r, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             store_split8(av1, av2, (DH / 8) * kTokCh + (row >> 3) * 128 + (row & 7) * 16, dd);
           }
+          TR(104);
           for (int hb = 0; hb < nrb; ++hb) {
             store_half(hb);
             accumulate_half(hb, n0 == 0);
@@ -465,11 +482,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             mbar_wait(&bar_b, ph_b);
             ph_b ^= 1;
             fence_after_sync();
+            TR(105 + hb);
           }
           load_dphi_to_g();
           fence_before_sync();
+          TR(107);
           input_gradient();  // red aliases the phi images: the accumulate MMAs above have completed
           __syncthreads();
+          TR(108);
         } else {
           // ---- K2: dv = phi_k dS ; dphi_k (already issued) ; dk
           float acc[RW];
@@ -501,14 +521,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             for (int c = 0; c < DH / 4; ++c)
               st4(dvb + (size_t)n * tok_stride + 4 * c, make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]));
           }
+          TR(204);
           mbar_wait(&bar_b, ph_b);
           ph_b ^= 1;
           fence_after_sync();
           load_dphi_to_g();
           fence_before_sync();
           __syncthreads();  // dv reduction buffer fully consumed
+          TR(205);
           input_gradient();
           __syncthreads();
+          TR(206);
         }
       }
       // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images
@@ -562,6 +585,7 @@ int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqk
   a.B = B; a.N = N; a.H = H; a.M = M; a.Mp = tc_bwd_mp(M); a.kind = kind; a.rot = rot; a.slots = slots;
   a.prescale = (float)pow((double)DH, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
+  a.trace = g_trace;
   const size_t smem = la_tc_bwd_smem_bytes(DH, M);
   int grid = (kNumSMs / H) * H;
   if (grid < H) grid = H;
@@ -582,5 +606,7 @@ int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqk
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }
+
+void set_tc_trace(long long* p) { g_trace = p; }
 
 }  // namespace erv

@@ -117,6 +117,9 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(int N, int bf16, int a
 
 using namespace erv;
 
+namespace erv { void set_tc_trace(long long* p); }
+extern "C" void erv_debug_set_trace(long long* device_buffer) { erv::set_tc_trace(device_buffer); }
+
 extern "C" int erv_debug_umma_timing(int N, int bf16, int a_mn_major, int b_mn_major, int iters, long long* cycles,
                                      void* stream) {
   ERV_CHECK_ARG(cycles && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0, "erv_debug_umma_timing: bad arguments");

@@ -52,6 +52,7 @@ SIGNATURES = {
     "erv_layernorm_bwd_workspace": (c_size_t, [_I, _I]),
     "erv_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
     "erv_debug_umma_gemm": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "erv_debug_set_trace": (None, [_P]),
     "erv_debug_umma_timing": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
 }
 

@@ -185,6 +185,9 @@ int erv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 int erv_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
                         int bf16, void* stream);
 /* SM clocks for `iters` back-to-back M=128 MMAs of width N issued by one thread (cycles: device int64). */
+/* Optional phase trace of the tensor-core backward: CTA 0 writes (tag, clock64) pairs into this device buffer of at
+ * least 2000 int64 (NULL disables). */
+void erv_debug_set_trace(long long* device_buffer);
 int erv_debug_umma_timing(int N, int bf16, int a_mn_major, int b_mn_major, int iters, long long* cycles,
                           void* stream);
 
