@@ -429,6 +429,9 @@ extern "C" size_t erv_linear_attention_workspace(int B, int N, int H, int head_d
 
 namespace erv {  // tensor-core path (erv_linattn_tc.cu)
 bool la_tc_eligible(int N, int DH, int M);
+bool la_tc2_eligible(int N, int DH, int M);  // two pairs per tile (erv_linattn_tc2.cu)
+int la_tc2_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
+                   const float* ta, const float* tb, int dtype, cudaStream_t st);
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
                   const float* ta, const float* tb, int dtype, cudaStream_t st);
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
@@ -450,6 +453,8 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   ERV_CHECK_ARG(!(bwd && rot == ERV_ROT_CIRCULANT) || dg_part, "%s: dg_part missing", fn);
   if (ws_bytes < wt_bytes(H, DH, M)) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (!bwd && la_tc2_eligible(N, DH, M))
+    return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, st);
   if (!bwd && la_tc_eligible(N, DH, M))
     return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
   if (bwd && la_tc_eligible(N, DH, M) && getenv("ERV_DISABLE_TC_BWD") == nullptr) {

@@ -125,6 +125,13 @@ ORACLE_CASES = [
     ("favor_plus", "most_general", 1, 257, 32, 2, 44),    # config 5, shortened (N=257, several key tiles)
     ("favor_plus", "rope", 2, 197, 768, 12, 64),          # ViT-B fixture dims, Dh=64
     ("relu", "circulant_string", 3, 50, 64, 8, 24),       # Dh=8
+    # short sequences: two (batch, head) pairs per tensor-core tile (erv_linattn_tc2.cu)
+    ("favor_plus", "rope", 3, 65, 32, 2, 44),             # odd batch, lone token, 64-feature instance
+    ("relu", "circulant_string", 5, 65, 32, 2, 100),      # 128-feature instance
+    ("favor_plus", None, 4, 50, 32, 2, 256),              # no lone token, ragged tile halves
+    ("relu", None, 3, 64, 32, 2, 44),                     # exactly half a tile per pair
+    ("favor_plus", "circulant_string", 2, 37, 32, 2, 200),
+    ("favor_plus", "rope", 1, 33, 32, 2, 128),            # single pair per head: second tile half empty
 ]
 
 
