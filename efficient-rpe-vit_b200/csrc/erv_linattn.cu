@@ -358,6 +358,13 @@ int la_grid(int B, int H) {
   return per_head * H;
 }
 
+// gradient slots per head for the Circulant table gradient: one per CTA of the fp32 kernels, two per CTA (one per pair
+// side) of the short-sequence tensor-core backward
+int la_slots(int B, int H) {
+  const int per_head = la_grid(B, H) / H;
+  return per_head + (per_head & 1);
+}
+
 static int prep_wt(const float* omega, float* wt, int H, int DH, int M, int Mp, int kind, cudaStream_t st) {
   size_t total = (size_t)H * Mp * (DH + 4);
   wt_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(omega, wt, H, DH, M, Mp,
@@ -419,7 +426,7 @@ using namespace erv;
 
 extern "C" int erv_circulant_slots(int B, int H) {
   if (B <= 0 || H <= 0) return 1;
-  return la_grid(B, H) / H;
+  return la_slots(B, H);
 }
 
 extern "C" size_t erv_linear_attention_workspace(int B, int N, int H, int head_dim, int M, int rot, int backward) {
@@ -432,6 +439,9 @@ bool la_tc_eligible(int N, int DH, int M);
 bool la_tc2_eligible(int N, int DH, int M);  // two pairs per tile (erv_linattn_tc2.cu)
 int la_tc2_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
                    const float* ta, const float* tb, int dtype, cudaStream_t st);
+int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
+                    int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
+                    int dtype, cudaStream_t st);
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
                   const float* ta, const float* tb, int dtype, cudaStream_t st);
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
@@ -458,9 +468,11 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   if (!bwd && la_tc_eligible(N, DH, M))
     return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
   if (bwd && la_tc_eligible(N, DH, M) && getenv("ERV_DISABLE_TC_BWD") == nullptr) {
-    const int slots = la_grid(B, H) / H;
+    const int slots = la_slots(B, H);
     float* dgp = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;
     if (dgp) ERV_CUDA(cudaMemsetAsync(dgp, 0, (size_t)H * slots * N * DH * sizeof(float), st));
+    if (la_tc2_eligible(N, DH, M) && getenv("ERV_DISABLE_TC2_BWD") == nullptr)
+      return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, st);
     return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
   }
   LaArgs a;
@@ -473,7 +485,7 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   rc = prep_wt(omega, (float*)ws, H, DH, M, a.g.Mp, kind, st);
   if (rc) return rc;
   const int grid = la_grid(B, H);
-  a.slots = grid / H;
+  a.slots = la_slots(B, H);
   if (bwd && a.dg_part) ERV_CUDA(cudaMemsetAsync(dg_part, 0, (size_t)H * a.slots * N * DH * sizeof(float), st));
   size_t smem = 0;
   int TT = pick_tt(DH, a.g, bwd, rot == ERV_ROT_CIRCULANT, &smem);

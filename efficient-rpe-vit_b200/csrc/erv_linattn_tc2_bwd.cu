@@ -1,0 +1,826 @@
+// Tensor-core backward of FAVOR+/ReLU linear attention for short sequences (33 <= N <= 65, head_dim 16,
+// num_features <= 256): two (batch, head) pairs per 128-row tile, the companion of erv_linattn_tc2.cu.
+//
+// Rows 0..63 of every tile belong to pair (2g, h), rows 64..127 to pair (2g+1, h); 512 threads = 4 per row, thread
+// (row, part) owns a quarter of the row's features in registers.  Three sweeps per group:
+//   K1  P = k W^T (3xTF32) ; phi_k ; S_pair[f][.] = phi_k^T [v|1]                          tcgen05 -> TMEM
+//   Q   P = q W^T ; phi_q ; den = phi_q . z ; a = [dO/den | -(dO.O)/den]
+//       dS_pair = phi_q^T a                                                               tcgen05, S's TMEM columns
+//       dphi_q  = a S^T  (both pairs in one K = 32 product: block-structured a image)     tcgen05, P's TMEM columns
+//       + a16 z^T (rank 1, registers) ; G = dphi (.) dphi/dP ; dq = G [W^T|1] ...          fp32 FMAs
+//   K2  P = k W^T ; phi_k ; dphi_k = v dS^T (+ dz) ; dv = phi_k [dS_A|dS_B]                tcgen05 ; dk as dq
+// bf16 hi/lo splits of both operands keep the contractions at ~2^-17; a split product takes two instructions by
+// concatenating along N: phi_hi x [b_hi | b_lo] and phi_lo x b_hi.  The feature images are written one 128-feature half
+// at a time (shared memory), each half's contraction running while the next half is stored.
+// When N = 65 the last token of each pair (the "lone" token) is handled outside the tiles: its feature rows are
+// computed by one warp per (pair, q|k), its rank-1 terms are folded into S / dS when they leave TMEM, and its own
+// gradients are three 256-thread reductions against S and dS.
+#include "erv_tc_common.cuh"
+
+namespace erv {
+
+struct LaTc2BwdArgs {
+  const void* qkv;
+  const void* out;
+  const void* dout;
+  void* dqkv;
+  const float* omega;
+  const float* ta;
+  const float* tb;
+  float* dg_part;  // [H][slots][N][DH], circulant only
+  int B, N, H, M, kind, rot, slots;
+  float prescale, inv_sqrt_m;
+};
+
+// raw 16-element row held as loaded (conversion to fp32 is deferred so the load stays in flight)
+template <typename T> struct RawRow;
+template <> struct RawRow<float> { float4 r[4]; };
+template <> struct RawRow<__nv_bfloat16> { uint4 r[2]; };
+__device__ __forceinline__ void load_raw(const float* p, RawRow<float>& w) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) w.r[c] = *reinterpret_cast<const float4*>(p + 4 * c);
+}
+__device__ __forceinline__ void load_raw(const __nv_bfloat16* p, RawRow<__nv_bfloat16>& w) {
+  w.r[0] = *reinterpret_cast<const uint4*>(p);
+  w.r[1] = *reinterpret_cast<const uint4*>(p + 8);
+}
+__device__ __forceinline__ void raw_to_f(const RawRow<float>& w, float (&x)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { x[4 * c] = w.r[c].x; x[4 * c + 1] = w.r[c].y; x[4 * c + 2] = w.r[c].z; x[4 * c + 3] = w.r[c].w; }
+}
+__device__ __forceinline__ void raw_to_f(const RawRow<__nv_bfloat16>& w, float (&x)[16]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t u[4] = {w.r[c].x, w.r[c].y, w.r[c].z, w.r[c].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[8 * c + 2 * i] = __uint_as_float(u[i] << 16);
+      x[8 * c + 2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+}
+
+// inverse of prologue_row for a gradient row dy (already multiplied by the Dh^-1/4 scale): rotate back, and for the
+// Circulant rotation accumulate this token's share of dL/dg into the CTA-private slot.
+template <typename T, int DH>
+__device__ __forceinline__ void prologue_row_bwd(const float (&dy)[DH], float (&dxr)[DH], int rot, const float* ta,
+                                                 const float* tb, int h, int n, int N, float* dg_slot,
+                                                 const T* x_raw_row) {
+  if (rot == ERV_ROT_ROPE) {
+#pragma unroll
+    for (int m = 0; m < DH / 2; ++m) {
+      const float c = __ldg(ta + (size_t)n * (DH / 2) + m), s = __ldg(tb + (size_t)n * (DH / 2) + m);
+      dxr[2 * m] = dy[2 * m] * c + dy[2 * m + 1] * s;
+      dxr[2 * m + 1] = dy[2 * m + 1] * c - dy[2 * m] * s;
+    }
+  } else if (rot == ERV_ROT_CIRCULANT) {
+    float g[DH];
+    load_row<float, DH>(ta + ((size_t)h * N + n) * DH, g);
+#pragma unroll
+    for (int bq = 0; bq < DH; ++bq) {
+      float a = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < DH; ++aa) a = fmaf(g[(aa - bq) & (DH - 1)], dy[aa], a);
+      dxr[bq] = a;
+    }
+    if (dg_slot != nullptr && n >= 1) {
+      float xr[DH];
+      load_row<T, DH>(x_raw_row, xr);
+#pragma unroll
+      for (int m = 0; m < DH; ++m) {
+        float a = 0.f;
+#pragma unroll
+        for (int aa = 0; aa < DH; ++aa) a = fmaf(dy[aa], xr[(aa - m) & (DH - 1)], a);
+        dg_slot[(size_t)n * DH + m] += a;  // slot private to this (CTA, pair side), row private to this thread
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dxr[d] = dy[d];
+  }
+}
+
+// NRB feature halves, CPH 8-feature chunks per thread and half: Mp = NRB * CPH * 32 is compile time so the per-thread
+// feature registers are statically indexed.
+template <typename T, int NRB, int CPH>
+__global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2BwdArgs p) {
+  constexpr int DH = 16, RW = DH + 4;
+  using C = TcCfg<DH>;
+  constexpr int nrb = NRB, HF = CPH * 32, FPH = CPH * 8, Mp = NRB * HF, NC = NRB * CPH;
+  constexpr uint32_t COL_P = 0, COL_S = 256, S_STRIDE = 64;
+  constexpr uint32_t wbytes = (uint32_t)(Mp / 8) * (DH / 4) * 128;
+  constexpr uint32_t s_ch = (uint32_t)(Mp / 8) * 128;
+  constexpr uint32_t halfbytes = 16 * kTokCh;  // one feature half, padded to 128 rows of the M dimension
+  constexpr uint32_t avbytes = 12 * kTokCh;    // per pair side: [hi(2) | special(1) | zero(1) | lo(2)] chunks
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_a, bar_b, bar_c;  // G1 / token- and feature-contractions / dphi
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float n2_s[128];
+  __shared__ float ex_s[4][128];   // row-max exchange
+  __shared__ float den_s[4][128];  // den partials
+  __shared__ float a16_s[128];
+  __shared__ __align__(16) float o_s[128][DH];
+  __shared__ __align__(16) float z_s[2][Mp];
+  __shared__ __align__(16) float dz_s[2][Mp];
+  __shared__ __align__(16) float lone_s[2][2][Mp];  // [q|k][pair side][feature]
+  __shared__ __align__(16) float lone_x[2][2][DH];  // prepared q / k rows of the lone tokens
+  __shared__ __align__(16) float lone_v[2][DH];
+  __shared__ __align__(16) float lone_do[2][DH];
+  __shared__ __align__(16) float lone_o[2][DH];
+  __shared__ float lone_a[2][DH + 1];
+  __shared__ float red1_s[16];
+  __shared__ float red2_s[16][DH + 1];
+  __shared__ float red3_s[16][2 * DH + 1];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, part = tid >> 7;
+  const int M = p.M, N = p.N, H = p.H, B = p.B;
+  const bool lone = N > 64;
+  const int Nm = lone ? N - 1 : N;
+  const int ks = (Nm + 15) >> 4;
+  const int side = row >> 6, n = row & 63;
+  const int ngroups = ((B + 1) >> 1) * H;
+  const int h = blockIdx.x % H;
+  const bool favor = p.kind == ERV_FEAT_FAVOR;
+
+  uint8_t* wh = smem;
+  uint8_t* wl = wh + wbytes;
+  uint8_t* xh = wl + wbytes;
+  uint8_t* xl = xh + C::X_BYTES;
+  uint8_t* phi1 = xl + C::X_BYTES;  // one feature half [128 tokens x 128 features], hi
+  uint8_t* phi2 = phi1 + halfbytes;  // lo
+  float* red = reinterpret_cast<float*>(phi1);  // [3][128][RW] fp32, aliases the feature images when they are idle
+  uint8_t* av = phi2 + halfbytes;    // [v|1] or [a|a16] rows, block-structured over the two pair sides
+  uint8_t* simg = av + avbytes;      // [S_A|S_B] hi, lo then [dS_A|dS_B]: byte(f, j) = (j/8)*s_ch + (f/8)*128 + (f%8)*16 + (j%8)*2
+  float* w32 = reinterpret_cast<float*>(simg + 8 * s_ch);  // [Mp][RW] fp32: W^T rows, column DH = 1 (rowsum)
+
+  // chunk c of this thread: half c / CPH, local chunk c % CPH
+  auto feat0 = [&](int c) { return (c / CPH) * HF + part * FPH + (c % CPH) * 8; };
+
+  for (int i = tid; i < (int)(avbytes / 16); i += kTcThreads) reinterpret_cast<uint4*>(av)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(2 * halfbytes / 16); i += kTcThreads) reinterpret_cast<uint4*>(phi1)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar_a, 1);
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_c, 1);
+    mbar_init_fence();
+  }
+  {  // W^T of this head: hi/lo TF32 images (rows f, K = Dh) and the fp32 rows [W^T | 1]
+    const float* om = p.omega + (size_t)h * DH * M;
+    for (int i = tid; i < Mp * DH; i += kTcThreads) {
+      const int d = i / Mp, f = i % Mp;
+      const float w = (f < M) ? __ldg(om + (size_t)d * M + f) : 0.f;
+      const float hi = to_tf32(w), lo = to_tf32(w - hi);
+      const uint32_t off = off_kmajor(f, d, 4, 4, C::X_LBO, C::X_SBO);
+      *reinterpret_cast<float*>(wh + off) = hi;
+      *reinterpret_cast<float*>(wl + off) = lo;
+      w32[f * RW + d] = w;
+    }
+    for (int i = tid; i < Mp * 4; i += kTcThreads) {
+      const int f = i >> 2, j = DH + (i & 3);
+      w32[f * RW + j] = (j == DH && f < M) ? 1.f : 0.f;
+    }
+  }
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t ph_a = 0, ph_b = 0, ph_c = 0;
+
+  const T* qkv = static_cast<const T*>(p.qkv);
+  const T* outp = static_cast<const T*>(p.out);
+  const T* dout = static_cast<const T*>(p.dout);
+  T* dqkv = static_cast<T*>(p.dqkv);
+  const uint32_t idesc_p = make_idesc(FMT_TF32, 128, Mp, false, false);
+  const uint32_t idesc_acc48 = make_idesc(FMT_BF16, 128, 48, true, true);  // S / dS (+)= phi^T rows
+  const uint32_t idesc_acc32 = make_idesc(FMT_BF16, 128, 32, true, true);
+  const uint32_t idesc_dphi = make_idesc(FMT_BF16, 128, Mp, false, false);  // dphi = rows [S_A ; S_B]^T
+  const uint32_t idesc_dv64 = make_idesc(FMT_BF16, 128, 64, false, true);   // dv = phi [dS_A|dS_B]
+  const uint32_t idesc_dv32 = make_idesc(FMT_BF16, 128, 32, false, true);
+  const float kLog2e = 1.4426950408889634f;
+  const float log2_c = log2f(p.inv_sqrt_m);
+  const uint32_t rowoff = (uint32_t)(row >> 3) * 128 + (row & 7) * 16;
+  uint8_t* av_side = av + (uint32_t)side * 6 * kTokCh;  // this row's pair side: chunks 0,1 hi | 2 special | 3 zero | 4,5 lo
+
+  // ---- global rows for the next sweep -> registers, consumed after the next barrier
+  RawRow<T> nx;
+  float4 nv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  load_raw(qkv, nx);  // defined contents; never used before a real prefetch
+  auto prefetch = [&](int g, int pass) {
+    if (g >= ngroups) return;
+    const int b2 = g / H, b = 2 * b2 + side;
+    const bool ok = b < B && n < Nm;
+    if (part == 0) {
+      if (ok) load_raw(qkv + qkv_off(b, n, pass == 1 ? 0 : 1, h, N, H, DH), nx);
+    } else if (part == 1) {
+      if (ok) {
+        if (pass == 1) load_raw(dout + out_off(b, n, h, N, H, DH), nx);
+        else load_raw(qkv + qkv_off(b, n, 2, h, N, H, DH), nx);
+      }
+    } else if (part == 2) {
+      if (ok && pass == 1) load_raw(outp + out_off(b, n, h, N, H, DH), nx);
+    } else if (lone && pass == 0) {  // warp (pair side, q|k): rows of the last token
+      const int lw = warp & 3, bb = 2 * b2 + (lw >> 1);
+      if (bb < B) {
+        load_raw(qkv + qkv_off(bb, N - 1, lw & 1, h, N, H, DH), nx);
+        if (lw & 1) {
+          if (lane < 4) nv4 = ld4(qkv + qkv_off(bb, N - 1, 2, h, N, H, DH) + 4 * lane);
+        } else {
+          if (lane < 4) nv4 = ld4(dout + out_off(bb, N - 1, h, N, H, DH) + 4 * lane);
+          else if (lane < 8) nv4 = ld4(outp + out_off(bb, N - 1, h, N, H, DH) + 4 * (lane - 4));
+        }
+      }
+    }
+  };
+
+  prefetch(blockIdx.x, 0);
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int b2 = g / H;
+    const int b = 2 * b2 + side;
+    const bool valid = b < B && n < Nm;
+    float* dg_slot = (p.rot == ERV_ROT_CIRCULANT && p.dg_part)
+                         ? p.dg_part + ((size_t)h * p.slots + (blockIdx.x / H) * 2) * N * DH : nullptr;  // + side * N * DH
+
+    for (int pass = 0; pass < 3; ++pass) {  // 0: K1 (build S), 1: Q (dS, dq), 2: K2 (dv, dk)
+      const int which = (pass == 1) ? 0 : 1;
+      // ---- step 1: consume the prefetched rows.  part 0 keeps the prepared q/k row, part 1 the dO row (Q sweep)
+      float rowv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
+      if (part == 0) {
+        float n2 = INFINITY;
+        if (valid) {
+          raw_to_f(nx, rowv);
+          prologue_row<DH>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+          n2 = 0.f;
+#pragma unroll
+          for (int a = 0; a < DH; ++a) n2 = fmaf(rowv[a], rowv[a], n2);
+          n2 *= 0.5f;
+        }
+        n2_s[row] = n2;
+        store_x_images<DH>(xh, xl, rowv, row);
+      } else if (part == 1) {
+        if (valid) raw_to_f(nx, rowv);
+        if (pass != 1) {  // [v_hi | 1 | 0 | v_lo]
+#pragma unroll
+          for (int c = 0; c < DH / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = rowv[8 * c + e];
+            store_split8(av_side, av_side + 4 * kTokCh, c * kTokCh + rowoff, ch);
+          }
+          *reinterpret_cast<uint4*>(av_side + 2 * kTokCh + rowoff) = make_uint4(valid ? 0x00003F80u : 0u, 0u, 0u, 0u);
+        }
+      } else if (part == 2) {
+        if (pass == 1) {
+          float o[DH];
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] = 0.f;
+          if (valid) raw_to_f(nx, o);
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) st4(&o_s[row][4 * c], make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+        }
+      } else if (lone && pass == 0) {  // feature rows of the lone tokens: warp = (pair side, q|k), lanes over features
+        const int lw = warp & 3, sp = lw >> 1, wq = lw & 1;  // wq: 0 = query, 1 = key
+        const bool ok = 2 * b2 + sp < B;
+        float x[DH];
+#pragma unroll
+        for (int a = 0; a < DH; ++a) x[a] = 0.f;
+        if (ok) {
+          raw_to_f(nx, x);
+          prologue_row<DH>(x, p.rot, p.ta, p.tb, h, N - 1, N, p.prescale);
+        }
+        float n2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < DH; ++a) n2 = fmaf(x[a], x[a], n2);
+        n2 *= 0.5f;
+        float pv[NC];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int f = lane + 32 * i;
+          const float* wr = w32 + f * RW;
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) {
+            const float4 a = ld4(wr + 4 * c);
+            acc = fmaf(x[4 * c], a.x, acc); acc = fmaf(x[4 * c + 1], a.y, acc);
+            acc = fmaf(x[4 * c + 2], a.z, acc); acc = fmaf(x[4 * c + 3], a.w, acc);
+          }
+          pv[i] = acc;
+          if (f < M) m = fmaxf(m, acc);
+        }
+        m = warp_max(m);
+        const float shift = fmaf(m + n2, kLog2e, -log2_c);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int f = lane + 32 * i;
+          float v = favor ? ex2_approx(fmaf(pv[i], kLog2e, -shift)) : fmaxf(pv[i], 0.f) * p.inv_sqrt_m;
+          if (f >= M || !ok) v = 0.f;
+          lone_s[wq][sp][f] = v;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) st4(&lone_x[wq][sp][4 * c], make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+        }
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wq == 1) {
+          if (lane < 4) st4(&lone_v[sp][4 * lane], ok ? nv4 : zero4);
+        } else {
+          if (lane < 4) st4(&lone_do[sp][4 * lane], ok ? nv4 : zero4);
+          else if (lane < 8) st4(&lone_o[sp][4 * (lane - 4)], ok ? nv4 : zero4);
+        }
+      }
+      fence_smem_to_async();
+      fence_before_sync();
+      __syncthreads();
+      // ---- lone-token gradients whose partial sums were written before this barrier
+      if (lone && pass > 0 && (tid == 32 || tid == 288)) {  // not the MMA-issuing thread
+        const int sp = tid >> 8, bb = 2 * b2 + sp;
+        if (bb < B) {
+          float* slot = dg_slot ? dg_slot + (size_t)sp * N * DH : nullptr;
+          if (pass == 1) {  // dq of the lone query
+            float acc[DH + 1];
+#pragma unroll
+            for (int j = 0; j <= DH; ++j) acc[j] = 0.f;
+            for (int w = 8 * sp; w < 8 * sp + 8; ++w)
+#pragma unroll
+              for (int j = 0; j <= DH; ++j) acc[j] += red2_s[w][j];
+            float dy[DH], dxr[DH];
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dy[d] = (favor ? acc[d] - lone_x[0][sp][d] * acc[DH] : acc[d]) * p.prescale;
+            const T* xraw = qkv + qkv_off(bb, N - 1, 0, h, N, H, DH);
+            prologue_row_bwd<T, DH>(dy, dxr, p.rot, p.ta, p.tb, h, N - 1, N, slot, xraw);
+            T* dst = dqkv + qkv_off(bb, N - 1, 0, h, N, H, DH);
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c) st4(dst + 4 * c, make_float4(dxr[4 * c], dxr[4 * c + 1], dxr[4 * c + 2], dxr[4 * c + 3]));
+          } else {  // dv and dk of the lone key
+            float acc[2 * DH + 1];
+#pragma unroll
+            for (int j = 0; j <= 2 * DH; ++j) acc[j] = 0.f;
+            for (int w = 8 * sp; w < 8 * sp + 8; ++w)
+#pragma unroll
+              for (int j = 0; j <= 2 * DH; ++j) acc[j] += red3_s[w][j];
+            T* dvp = dqkv + qkv_off(bb, N - 1, 2, h, N, H, DH);
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c) st4(dvp + 4 * c, make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]));
+            float dy[DH], dxr[DH];
+#pragma unroll
+            for (int d = 0; d < DH; ++d)
+              dy[d] = (favor ? acc[DH + d] - lone_x[1][sp][d] * acc[2 * DH] : acc[DH + d]) * p.prescale;
+            const T* xraw = qkv + qkv_off(bb, N - 1, 1, h, N, H, DH);
+            prologue_row_bwd<T, DH>(dy, dxr, p.rot, p.ta, p.tb, h, N - 1, N, slot, xraw);
+            T* dst = dqkv + qkv_off(bb, N - 1, 1, h, N, H, DH);
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c) st4(dst + 4 * c, make_float4(dxr[4 * c], dxr[4 * c + 1], dxr[4 * c + 2], dxr[4 * c + 3]));
+          }
+        }
+      }
+      // ---- G1: P = x W^T (3xTF32)
+      if (tid == 0) {
+        fence_after_sync();
+        bool acc = false;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint8_t* xa = (term == 1) ? xl : xh;
+          const uint8_t* wb = (term == 2) ? wl : wh;
+#pragma unroll
+          for (int s = 0; s < DH / 8; ++s) {
+            mma_tf32(tm + COL_P, make_desc(smem_u32(xa) + s * 2 * C::X_LBO, C::X_LBO, C::X_SBO),
+                     make_desc(smem_u32(wb) + s * 2 * C::X_LBO, C::X_LBO, C::X_SBO), idesc_p, acc);
+            acc = true;
+          }
+        }
+        commit(&bar_a);
+      }
+      mbar_wait(&bar_a, ph_a);
+      ph_a ^= 1;
+      fence_after_sync();
+      // ---- P -> registers, row max, phi (kept in pr as fp32 bit patterns)
+      uint32_t pr[NC][8];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) tmem_ld8_nowait(tm + lane_off + COL_P + feat0(c), pr[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) tmem_wait_ld8(pr[c]);
+      if (favor) {
+        float m_part = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (feat0(c) + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+        ex_s[part][row] = m_part;
+      }
+      fence_before_sync();
+      __syncthreads();  // all P reads are done: the P columns may be overwritten (dphi)
+      if (pass == 2 && tid == 0) {  // K2: dphi_k = v [dS_A ; dS_B]^T can start as soon as P has been consumed
+        fence_after_sync();
+        bool acc = false;
+        for (int sp = 0; sp < 2; ++sp)
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a_off = (uint32_t)(sp * 6 + (term == 2 ? 4 : 0)) * kTokCh;
+            const uint32_t b_off = (uint32_t)((term == 1 ? 4 : 0) + 2 * sp) * s_ch;
+            mma_f16(tm + COL_P, make_desc(smem_u32(av) + a_off, kTokCh, 128), make_desc(smem_u32(simg) + b_off, s_ch, 128),
+                    idesc_dphi, acc);
+            acc = true;
+          }
+        commit(&bar_c);
+      }
+      {
+        float mx = 0.f;
+        if (favor) mx = fmaxf(fmaxf(ex_s[0][row], ex_s[1][row]), fmaxf(ex_s[2][row], ex_s[3][row]));
+        const float n2 = n2_s[row];
+        const float shift = fmaf(mx + n2, kLog2e, -log2_c);
+        const float scale = (n2 < INFINITY) ? p.inv_sqrt_m : 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int f0 = feat0(c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pv = __uint_as_float(pr[c][i]);
+            float v = favor ? ex2_approx(fmaf(pv, kLog2e, -shift)) : fmaxf(pv, 0.f) * scale;
+            if (f0 + i >= M) v = 0.f;
+            pr[c][i] = __float_as_uint(v);
+          }
+        }
+      }
+      // stores one feature half of the values held in pr into the phi images
+      auto store_half = [&](int hb) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c / CPH == hb) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(pr[c][i]);
+            store_split8(phi1, phi2, (uint32_t)(part * CPH + (c % CPH)) * kTokCh + rowoff, v);
+          }
+      };
+      // D[COL_S + (sp*nrb + hb)*64] = phi_half^T rows of pair side sp (rows image = av); one thread
+      auto issue_accumulate = [&](int hb) {
+        for (int sp = 0; sp < 2; ++sp) {
+          const uint32_t d = tm + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE;
+          for (int s = 0; s < ks; ++s) {
+            const uint32_t st = (uint32_t)(sp * 4 + s) * 256;
+            const uint64_t bd = make_desc(smem_u32(av) + (uint32_t)sp * 6 * kTokCh + st, 128, kTokCh);
+            mma_f16(d, make_desc(smem_u32(phi1) + st, 128, kTokCh), bd, idesc_acc48, s > 0);
+            mma_f16(d, make_desc(smem_u32(phi2) + st, 128, kTokCh), bd, idesc_acc32, true);
+          }
+        }
+        commit(&bar_b);
+      };
+      // 4-way reduction over the threads of a row; result valid in part 0
+      auto reduce_rows = [&](float (&acc)[RW]) {
+        if (part > 0) {
+#pragma unroll
+          for (int j = 0; j < RW; j += 4)
+            st4(red + ((size_t)(part - 1) * 128 + row) * RW + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        }
+        __syncthreads();
+        if (part == 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int j = 0; j < RW; j += 4) {
+              const float4 v = ld4(red + ((size_t)q * 128 + row) * RW + j);
+              acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+            }
+        }
+      };
+      // G (in pr) x [W^T | 1]: this thread's partial sums
+      auto gradient_partial = [&](float (&acc)[RW]) {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int f0 = feat0(c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gq = __uint_as_float(pr[c][i]);
+            const float* wr = w32 + (f0 + i) * RW;
+#pragma unroll
+            for (int cd = 0; cd < RW / 4; ++cd) {
+              const float4 a = ld4(wr + 4 * cd);
+              acc[4 * cd] = fmaf(gq, a.x, acc[4 * cd]);
+              acc[4 * cd + 1] = fmaf(gq, a.y, acc[4 * cd + 1]);
+              acc[4 * cd + 2] = fmaf(gq, a.z, acc[4 * cd + 2]);
+              acc[4 * cd + 3] = fmaf(gq, a.w, acc[4 * cd + 3]);
+            }
+          }
+        }
+      };
+      // reduced sums (part 0) -> gradient wrt the raw q/k row, written to global memory
+      auto store_input_gradient = [&](const float (&acc)[RW]) {
+        if (part == 0 && valid) {
+          float dy[DH], dxr[DH];
+#pragma unroll
+          for (int d = 0; d < DH; ++d) dy[d] = (favor ? acc[d] - rowv[d] * acc[DH] : acc[d]) * p.prescale;
+          const T* xraw = qkv + qkv_off(b, n, which, h, N, H, DH);
+          prologue_row_bwd<T, DH>(dy, dxr, p.rot, p.ta, p.tb, h, n, N, dg_slot ? dg_slot + (size_t)side * N * DH : nullptr, xraw);
+          T* dst = dqkv + qkv_off(b, n, which, h, N, H, DH);
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) st4(dst + 4 * c, make_float4(dxr[4 * c], dxr[4 * c + 1], dxr[4 * c + 2], dxr[4 * c + 3]));
+        }
+      };
+      // dphi (TMEM, P columns) + rank-1 term -> G = dphi (.) dphi/dP, in place in pr
+      auto load_dphi_to_g = [&](const float* rank1, float rscale) {  // dphi[f] += rscale * rank1[f]
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t r[8];
+          tmem_ld8_nowait(tm + lane_off + COL_P + feat0(c), r);
+          const float4 za = ld4(rank1 + feat0(c)), zb = ld4(rank1 + feat0(c) + 4);
+          const float zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+          tmem_wait_ld8(r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ph_v = __uint_as_float(pr[c][i]);
+            const float dph = fmaf(rscale, zz[i], __uint_as_float(r[i]));
+            const float gq = favor ? dph * ph_v : (ph_v > 0.f ? dph * p.inv_sqrt_m : 0.f);
+            pr[c][i] = __float_as_uint(gq);
+          }
+        }
+      };
+
+      if (pass == 0) {
+        // ---- K1: S(pair, hb) = phi_k^T [v|1]
+        for (int hb = 0; hb < nrb; ++hb) {
+          store_half(hb);
+          fence_smem_to_async();
+          fence_before_sync();
+          __syncthreads();
+          if (tid == 0) {
+            fence_after_sync();
+            issue_accumulate(hb);
+          }
+          if (hb == nrb - 1) prefetch(g, 1);
+          mbar_wait(&bar_b, ph_b);
+          ph_b ^= 1;
+          fence_after_sync();
+        }
+      } else if (pass == 1) {
+        // ---- Q: den, a, dS = phi_q^T a, dphi_q = a S^T
+        float den_part = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float4 za = ld4(&z_s[side][feat0(c)]), zb = ld4(&z_s[side][feat0(c) + 4]);
+          den_part = fmaf(__uint_as_float(pr[c][0]), za.x, den_part); den_part = fmaf(__uint_as_float(pr[c][1]), za.y, den_part);
+          den_part = fmaf(__uint_as_float(pr[c][2]), za.z, den_part); den_part = fmaf(__uint_as_float(pr[c][3]), za.w, den_part);
+          den_part = fmaf(__uint_as_float(pr[c][4]), zb.x, den_part); den_part = fmaf(__uint_as_float(pr[c][5]), zb.y, den_part);
+          den_part = fmaf(__uint_as_float(pr[c][6]), zb.z, den_part); den_part = fmaf(__uint_as_float(pr[c][7]), zb.w, den_part);
+        }
+        den_s[part][row] = den_part;
+        store_half(0);  // does not depend on den: overlaps the exchange
+        __syncthreads();
+        if (part == 1) {
+          const float r = 1.0f / ((den_s[0][row] + den_s[1][row]) + (den_s[2][row] + den_s[3][row]) + kEps);
+          float dot = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) dot = fmaf(rowv[d], o_s[row][d], dot);
+#pragma unroll
+          for (int c = 0; c < DH / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = rowv[8 * c + e] * r;
+            store_split8(av_side, av_side + 4 * kTokCh, c * kTokCh + rowoff, ch);
+          }
+          const float a16 = valid ? -dot * r : 0.f;
+          a16_s[row] = a16;
+          const uint32_t hi = __float_as_uint(a16) & 0xffff0000u;
+          const float lo = a16 - __uint_as_float(hi);
+          *reinterpret_cast<uint4*>(av_side + 2 * kTokCh + rowoff) =
+              make_uint4((hi >> 16) | (__float_as_uint(lo) & 0xffff0000u), 0u, 0u, 0u);  // [a16_hi, a16_lo]
+        }
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          fence_after_sync();
+          issue_accumulate(0);
+          // dphi_q for the whole row, into the (consumed) P columns: K = [pair A's 16 | pair B's 16]
+          bool acc = false;
+          for (int sp = 0; sp < 2; ++sp)
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t a_off = (uint32_t)(sp * 6 + (term == 2 ? 4 : 0)) * kTokCh;
+              const uint32_t b_off = (uint32_t)((term == 1 ? 4 : 0) + 2 * sp) * s_ch;
+              mma_f16(tm + COL_P, make_desc(smem_u32(av) + a_off, kTokCh, 128), make_desc(smem_u32(simg) + b_off, s_ch, 128),
+                      idesc_dphi, acc);
+              acc = true;
+            }
+          commit(&bar_c);
+        }
+        mbar_wait(&bar_b, ph_b);
+        ph_b ^= 1;
+        fence_after_sync();
+        if (nrb > 1) {
+          store_half(1);
+          fence_smem_to_async();
+          fence_before_sync();
+          __syncthreads();
+          if (tid == 0) {
+            fence_after_sync();
+            issue_accumulate(1);
+          }
+        }
+        mbar_wait(&bar_c, ph_c);
+        ph_c ^= 1;
+        fence_after_sync();
+        load_dphi_to_g(&z_s[side][0], a16_s[row]);
+        fence_before_sync();
+        float acc[RW];
+        gradient_partial(acc);
+        if (nrb > 1) {
+          mbar_wait(&bar_b, ph_b);  // the second half's contraction has read the feature images: red may alias them
+          ph_b ^= 1;
+          fence_after_sync();
+        }
+        reduce_rows(acc);
+        store_input_gradient(acc);
+        prefetch(g, 2);
+      } else {
+        // ---- K2: dv = phi_k [dS_A|dS_B] ; dphi_k (already issued) ; dk
+        for (int hb = 0; hb < nrb; ++hb) {
+          store_half(hb);
+          fence_smem_to_async();
+          fence_before_sync();
+          __syncthreads();
+          if (tid == 0) {
+            fence_after_sync();
+            for (int s = 0; s < HF / 16; ++s) {
+              const uint64_t bd = make_desc(smem_u32(simg) + (uint32_t)(hb * (HF / 16) + s) * 256, 128, s_ch);
+              mma_f16(tm + COL_S, make_desc(smem_u32(phi1) + (uint32_t)s * 2 * kTokCh, kTokCh, 128), bd, idesc_dv64, hb > 0 || s > 0);
+              mma_f16(tm + COL_S, make_desc(smem_u32(phi2) + (uint32_t)s * 2 * kTokCh, kTokCh, 128), bd, idesc_dv32, true);
+            }
+            commit(&bar_b);
+          }
+          if (hb < nrb - 1) {
+            mbar_wait(&bar_b, ph_b);
+            ph_b ^= 1;
+            fence_after_sync();
+          }
+        }
+        mbar_wait(&bar_c, ph_c);
+        ph_c ^= 1;
+        fence_after_sync();
+        load_dphi_to_g(&dz_s[side][0], 1.0f);
+        fence_before_sync();
+        float acc[RW];
+        gradient_partial(acc);
+        mbar_wait(&bar_b, ph_b);
+        ph_b ^= 1;
+        fence_after_sync();
+        reduce_rows(acc);
+        store_input_gradient(acc);
+        prefetch(g + gridDim.x, 0);
+        if (part == 0) {  // dv rows: hi-part + lo-part columns of this row's pair
+          float a0[16], a1[16];
+          tmem_ld16(tm + lane_off + COL_S + 16 * side, a0);
+          tmem_ld16(tm + lane_off + COL_S + 32 + 16 * side, a1);
+          if (valid) {
+            T* dvp = dqkv + qkv_off(b, n, 2, h, N, H, DH);
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c)
+              st4(dvp + 4 * c, make_float4(a0[4 * c] + a1[4 * c], a0[4 * c + 1] + a1[4 * c + 1], a0[4 * c + 2] + a1[4 * c + 2],
+                                           a0[4 * c + 3] + a1[4 * c + 3]));
+          }
+        }
+        fence_before_sync();
+        __syncthreads();  // red (feature images) and the TMEM columns are reused by the next group
+      }
+      // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images; lone-token terms
+      if (pass < 2) {
+        const int sp = part >> 1, hb = part & 1, f = hb * HF + row;
+        const bool own = hb < nrb && row < HF;  // warp-uniform
+        float sv[DH], zz = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) sv[d] = 0.f;
+        float pq = 0.f, pk = 0.f;
+        if (own) {
+          float d0[32], d1[16];
+          tmem_ld32(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE, d0);
+          tmem_ld16(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE + 32, d1);
+#pragma unroll
+          for (int d = 0; d < DH; ++d) sv[d] = d0[d] + d1[d];
+          zz = (pass == 0) ? d0[DH] : d0[DH] + d0[DH + 1];
+          if (lone) {
+            pq = lone_s[0][sp][f];
+            pk = lone_s[1][sp][f];
+            if (pass == 0) {  // rank-1 term of the last key
+#pragma unroll
+              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pk, lone_v[sp][d], sv[d]);
+              zz += pk;
+            } else {  // rank-1 term of the last query
+#pragma unroll
+              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pq, lone_a[sp][d], sv[d]);
+              zz = fmaf(pq, lone_a[sp][DH], zz);
+            }
+          }
+          if (pass == 0) z_s[sp][f] = zz; else dz_s[sp][f] = zz;
+#pragma unroll
+          for (int c = 0; c < DH / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
+            store_split8(simg + (uint32_t)(2 * sp + c) * s_ch, simg + (uint32_t)(4 + 2 * sp + c) * s_ch,
+                         (uint32_t)(f >> 3) * 128 + (f & 7) * 16, ch);
+          }
+        }
+        if (lone) {
+          if (pass == 0) {
+            const float s = warp_sum(pq * zz);  // den of the lone query
+            if (lane == 0) red1_s[warp] = s;
+            fence_smem_to_async();
+            __syncthreads();
+            float den = kEps;
+            for (int w = 8 * sp; w < 8 * sp + 8; ++w) den += red1_s[w];
+            const float r = 1.0f / den;
+            float dot = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dot = fmaf(lone_do[sp][d], lone_o[sp][d], dot);
+            const float a16 = -dot * r;
+            float dph = a16 * zz;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dph = fmaf(lone_do[sp][d] * r, sv[d], dph);
+            const float gq = own ? (favor ? dph * pq : (pq > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
+            const float* wr = w32 + (own ? f : 0) * RW;
+#pragma unroll
+            for (int j = 0; j <= DH; ++j) {
+              const float t = warp_sum(gq * wr[j]);
+              if (lane == 0) red2_s[warp][j] = t;
+            }
+            if ((tid & 255) == 0) {
+#pragma unroll
+              for (int d = 0; d < DH; ++d) lone_a[sp][d] = lone_do[sp][d] * r;
+              lone_a[sp][DH] = a16;
+            }
+          } else {
+            float dph = zz;  // dphi of the lone key: v_L . dS[f] + dz[f]
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dph = fmaf(lone_v[sp][d], sv[d], dph);
+            const float gk = own ? (favor ? dph * pk : (pk > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
+            const float* wr = w32 + (own ? f : 0) * RW;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) {
+              const float t = warp_sum(pk * sv[d]);
+              if (lane == 0) red3_s[warp][d] = t;
+            }
+#pragma unroll
+            for (int j = 0; j <= DH; ++j) {
+              const float t = warp_sum(gk * wr[j]);
+              if (lane == 0) red3_s[warp][DH + j] = t;
+            }
+          }
+        }
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+static int tc2b_mp(int M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
+
+size_t la_tc2_bwd_smem_bytes(int M) {
+  const int Mp = tc2b_mp(M);
+  const size_t wbytes = (size_t)(Mp / 8) * 4 * 128, xbytes = 16 * 4 * 128;
+  return 2 * wbytes + 2 * xbytes + 2 * 16 * (size_t)kTokCh + 12 * (size_t)kTokCh + 8 * (size_t)(Mp / 8) * 128 +
+         (size_t)Mp * 20 * sizeof(float) + 128;
+}
+
+int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
+                    int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
+                    int dtype, cudaStream_t st) {
+  LaTc2BwdArgs a;
+  a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.omega = omega; a.ta = ta; a.tb = tb; a.dg_part = dg_part;
+  a.B = B; a.N = N; a.H = H; a.M = M; a.kind = kind; a.rot = rot; a.slots = slots;
+  a.prescale = (float)pow(16.0, -0.25);
+  a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
+  const int Mp = tc2b_mp(M);
+  const size_t smem = la_tc2_bwd_smem_bytes(M);
+  const int ngroups = ((B + 1) / 2) * H;
+  int grid = (kNumSMs / H) * H;
+  if (grid < H) grid = H;
+  if (grid > ngroups) grid = ngroups;
+  if (dg_part != nullptr && 2 * (grid / H) > slots) grid = (slots / 2) * H;  // two gradient slots per CTA
+  if (grid < H) { set_error("tensor-core backward: %d gradient slots are too few", slots); return ERV_E_INVALID; }
+#define TC2B_LAUNCH(TT, NRB_, CPH_)                                              \
+  do {                                                                           \
+    ERV_CUDA(allow_smem(la_tc2_bwd_kernel<TT, NRB_, CPH_>, smem));               \
+    la_tc2_bwd_kernel<TT, NRB_, CPH_><<<grid, kTcThreads, smem, st>>>(a);        \
+  } while (0)
+  if (dtype == ERV_F32) {
+    if (Mp == 64) TC2B_LAUNCH(float, 1, 2); else if (Mp == 128) TC2B_LAUNCH(float, 1, 4); else TC2B_LAUNCH(float, 2, 4);
+  } else {
+    if (Mp == 64) TC2B_LAUNCH(__nv_bfloat16, 1, 2); else if (Mp == 128) TC2B_LAUNCH(__nv_bfloat16, 1, 4); else TC2B_LAUNCH(__nv_bfloat16, 2, 4);
+  }
+#undef TC2B_LAUNCH
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
+
+}  // namespace erv

@@ -16,6 +16,7 @@ int launch_feature_map(const void* x, void* dx, size_t sb, size_t sh, size_t sn,
                        int ldphi, const float* wt, int B, int N, int H, int DH, int M, int kind, int prep,
                        float prescale, int dtype, bool bwd, cudaStream_t st);
 int la_grid(int B, int H);
+int la_slots(int B, int H);
 size_t wt_bytes(int H, int DH, int M);
 int prep_wt_public(const float* omega, float* wt, int H, int DH, int M, int kind, cudaStream_t st);
 
@@ -795,7 +796,7 @@ extern "C" int erv_softmax_attention_bwd(const void* qkv, const void* out, const
   const size_t plane = (size_t)B * H * N * head_dim;
   float* rows = (float*)workspace;
   float* drows = (float*)((char*)workspace + erv_softmax_attention_workspace(B, N, H, head_dim, rot, 0));
-  const int slots = la_grid(B, H) / H;
+  const int slots = la_slots(B, H);
   RotPackArgs r{qkv, dqkv, rows, drows, tab_a, tab_b, rot == ERV_ROT_CIRCULANT ? dg_part : nullptr, B, N, H, rot, slots};
   rc = dtype == ERV_F32 ? rot_pack<float, false>(r, head_dim, st) : rot_pack<__nv_bfloat16, false>(r, head_dim, st);
   if (rc) return rc;
