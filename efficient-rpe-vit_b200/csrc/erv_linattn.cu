@@ -438,10 +438,11 @@ namespace erv {  // tensor-core path (erv_linattn_tc.cu)
 bool la_tc_eligible(int N, int DH, int M);
 bool la_tc2_eligible(int N, int DH, int M);  // two pairs per tile (erv_linattn_tc2.cu)
 int la_tc2_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
-                   const float* ta, const float* tb, int dtype, cudaStream_t st);
+                   const float* ta, const float* tb, int dtype, float* state, cudaStream_t st);
+int tc2_mp(int M);
 int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
-                    int dtype, cudaStream_t st);
+                    int dtype, const float* state, cudaStream_t st);
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
                   const float* ta, const float* tb, int dtype, cudaStream_t st);
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
@@ -449,9 +450,15 @@ int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqk
                    int dtype, cudaStream_t st);
 }  // namespace erv
 
+// Floats of the [S|z] state the forward saves for the backward (0: these shapes recompute S in the backward).
+extern "C" size_t erv_linear_attention_state_floats(int B, int N, int H, int head_dim, int M) {
+  if (B <= 0 || H <= 0 || !erv::la_tc2_eligible(N, head_dim, M)) return 0;
+  return (size_t)B * H * (head_dim + 1) * erv::tc2_mp(M);
+}
+
 static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, void* dqkv, const float* omega, int B,
                      int N, int H, int DH, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part,
-                     int dtype, void* ws, size_t ws_bytes, void* stream) {
+                     int dtype, float* state, void* ws, size_t ws_bytes, void* stream) {
   const char* fn = bwd ? "erv_linear_attention_bwd" : "erv_linear_attention_fwd";
   int rc = check_common(fn, B, N, H, DH, M, dtype);
   if (rc) return rc;
@@ -464,7 +471,7 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   if (ws_bytes < wt_bytes(H, DH, M)) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   if (!bwd && la_tc2_eligible(N, DH, M))
-    return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, st);
+    return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, state, st);
   if (!bwd && la_tc_eligible(N, DH, M))
     return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
   if (bwd && la_tc_eligible(N, DH, M) && getenv("ERV_DISABLE_TC_BWD") == nullptr) {
@@ -472,7 +479,7 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
     float* dgp = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;
     if (dgp) ERV_CUDA(cudaMemsetAsync(dgp, 0, (size_t)H * slots * N * DH * sizeof(float), st));
     if (la_tc2_eligible(N, DH, M) && getenv("ERV_DISABLE_TC2_BWD") == nullptr)
-      return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, st);
+      return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
     return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
   }
   LaArgs a;
@@ -506,17 +513,18 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
 
 extern "C" int erv_linear_attention_fwd(const void* qkv, void* out, const float* omega, int B, int N, int H,
                                         int head_dim, int M, int kind, int rot, const float* tab_a, const float* tab_b,
-                                        int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+                                        int dtype, float* kv_state, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
   return la_launch(false, qkv, out, nullptr, nullptr, omega, B, N, H, head_dim, M, kind, rot, tab_a, tab_b, nullptr,
-                   dtype, workspace, workspace_bytes, stream);
+                   dtype, kv_state, workspace, workspace_bytes, stream);
 }
 
 extern "C" int erv_linear_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv,
                                         const float* omega, int B, int N, int H, int head_dim, int M, int kind, int rot,
                                         const float* tab_a, const float* tab_b, float* dg_part, int dtype,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
+                                        const float* kv_state, void* workspace, size_t workspace_bytes, void* stream) {
   return la_launch(true, qkv, const_cast<void*>(out), dout, dqkv, omega, B, N, H, head_dim, M, kind, rot, tab_a, tab_b,
-                   dg_part, dtype, workspace, workspace_bytes, stream);
+                   dg_part, dtype, const_cast<float*>(kv_state), workspace, workspace_bytes, stream);
 }
 
 // x [B,H,N,DH] fp32 contiguous; workspace-free variants allocate nothing: the W^T staging buffer is the

@@ -319,6 +319,7 @@ int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, 
   a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = M <= 64 ? 64 : (M <= 128 ? 128 : 256); a.kind = kind; a.rot = rot;
   a.prescale = (float)pow((double)DH, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
+  a.state = nullptr;
   const size_t smem = la_tc_smem_bytes(DH, a.Mp16);
   int grid = (kNumSMs / H) * H;  // multiple of H: each CTA stays on one head (W images staged once)
   if (grid < H) grid = H;

@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     // ---- S (TMEM, lanes = features) -> S image for G4, z, lone-token terms.  Thread = (pair side, block, feature).
     {
       const int sp = part >> 1, rb = part & 1, f = rb * 128 + row;
-      float acc17[DH + 1];
+      float acc32[32];  // lone query read-out partials: [0, DH) numerator, DH denominator, rest padding
 #pragma unroll
-      for (int j = 0; j <= DH; ++j) acc17[j] = 0.f;
+      for (int j = 0; j < 32; ++j) acc32[j] = 0.f;
       if (rb < nrb && f < Mp) {  // warp-uniform
         float d0[32], d1[16], sv[DH];
         tmem_ld32(tm + lane_off + COL_S + (uint32_t)(sp * 2 + rb) * S_STRIDE, d0);
@@ -338,19 +338,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
           store_split8(vs + (uint32_t)(2 * sp + c) * s_ch, vs + (uint32_t)(4 + 2 * sp + c) * s_ch,
                        (uint32_t)(f >> 3) * 128 + (f & 7) * 16, ch);
         }
+        if (p.state != nullptr && 2 * b2 + sp < B) {  // [S|z] of this pair, d-major so that a warp writes 128 B lines
+          float* sp_out = p.state + ((size_t)(2 * b2 + sp) * H + h) * (DH + 1) * Mp + f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) sp_out[(size_t)d * Mp] = sv[d];
+          sp_out[(size_t)DH * Mp] = z;
+        }
         if (lone) {  // the last query's read-out against the finished S
           const float pq = lone_s[0][sp][f];
 #pragma unroll
-          for (int d = 0; d < DH; ++d) acc17[d] = pq * sv[d];
-          acc17[DH] = pq * z;
+          for (int d = 0; d < DH; ++d) acc32[d] = pq * sv[d];
+          acc32[DH] = pq * z;
         }
       }
       if (lone) {
-#pragma unroll
-        for (int j = 0; j <= DH; ++j) {
-          const float s = warp_sum(acc17[j]);
-          if (lane == 0) red_s[warp][j] = s;
-        }
+        const float t = warp_sum32(acc32);  // lane j holds the warp total of partial j
+        if (lane <= DH) red_s[warp][lane] = t;
       }
     }
     fence_smem_to_async();
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
-static int tc2_mp(int M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
+int tc2_mp(int M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
 
 size_t la_tc2_smem_bytes(int Mp) {
   const size_t nrb = (Mp + 127) / 128;
@@ -426,12 +429,13 @@ bool la_tc2_eligible(int N, int DH, int M) {
 }
 
 int la_tc2_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
-                   const float* ta, const float* tb, int dtype, cudaStream_t st) {
+                   const float* ta, const float* tb, int dtype, float* state, cudaStream_t st) {
   LaTcArgs a;
   a.qkv = qkv; a.out = out; a.omega = omega; a.ta = ta; a.tb = tb;
   a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = tc2_mp(M); a.kind = kind; a.rot = rot;
   a.prescale = (float)pow(16.0, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
+  a.state = state;
   const size_t smem = la_tc2_smem_bytes(a.Mp16);
   const int ngroups = ((B + 1) / 2) * H;
   int grid = (kNumSMs / H) * H;  // multiple of H: each CTA stays on one head (W images staged once)

@@ -28,6 +28,7 @@ struct LaTc2BwdArgs {
   const float* ta;
   const float* tb;
   float* dg_part;  // [H][slots][N][DH], circulant only
+  const float* state;  // optional [B*H][DH+1][Mp]: [S|z] saved by the forward; the K1 sweep is skipped when present
   int B, N, H, M, kind, rot, slots;
   float prescale, inv_sqrt_m;
 };
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   const int ngroups = ((B + 1) >> 1) * H;
   const int h = blockIdx.x % H;
   const bool favor = p.kind == ERV_FEAT_FAVOR;
+  const bool have_state = p.state != nullptr;
 
   uint8_t* wh = smem;
   uint8_t* wl = wh + wbytes;
@@ -214,9 +216,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
     const int b2 = g / H, b = 2 * b2 + side;
     const bool ok = b < B && n < Nm;
     if (part == 0) {
-      if (ok) load_raw(qkv + qkv_off(b, n, pass == 1 ? 0 : 1, h, N, H, DH), nx);
+      if (ok && !(pass == 0 && have_state)) load_raw(qkv + qkv_off(b, n, pass == 1 ? 0 : 1, h, N, H, DH), nx);
     } else if (part == 1) {
-      if (ok) {
+      if (ok && !(pass == 0 && have_state)) {
         if (pass == 1) load_raw(dout + out_off(b, n, h, N, H, DH), nx);
         else load_raw(qkv + qkv_off(b, n, 2, h, N, H, DH), nx);
       }
@@ -250,7 +252,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       float rowv[DH];
 #pragma unroll
       for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
-      if (part == 0) {
+      const bool skip = pass == 0 && have_state;  // S comes from the forward: no K1 sweep
+      if (skip) {
+        // only the lone-token rows (part 3 below) are prepared
+      } else if (part == 0) {
         float n2 = INFINITY;
         if (valid) {
           raw_to_f(nx, rowv);
@@ -283,7 +288,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
           for (int c = 0; c < DH / 4; ++c) st4(&o_s[row][4 * c], make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
         }
-      } else if (lone && pass == 0) {  // feature rows of the lone tokens: warp = (pair side, q|k), lanes over features
+      }
+      if (part == 3 && lone && pass == 0) {  // feature rows of the lone tokens: warp = (pair side, q|k), lanes over features
         const int lw = warp & 3, sp = lw >> 1, wq = lw & 1;  // wq: 0 = query, 1 = key
         const bool ok = 2 * b2 + sp < B;
         float x[DH];
@@ -379,6 +385,116 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           }
         }
       }
+      // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images; lone-token terms
+      auto sweep_tail = [&](const bool from_state, const float (&st)[DH + 1]) {
+        const int sp = part >> 1, hb = part & 1, f = hb * HF + row;
+        const bool own = hb < nrb && row < HF;  // warp-uniform
+        float sv[DH], zz = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) sv[d] = 0.f;
+        float pq = 0.f, pk = 0.f;
+        if (own) {
+          if (from_state) {  // the forward's finished [S|z] (lone key included)
+#pragma unroll
+            for (int d = 0; d < DH; ++d) sv[d] = st[d];
+            zz = st[DH];
+          } else {
+            float d0[32], d1[16];
+            tmem_ld32(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE, d0);
+            tmem_ld16(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE + 32, d1);
+#pragma unroll
+            for (int d = 0; d < DH; ++d) sv[d] = d0[d] + d1[d];
+            zz = (pass == 0) ? d0[DH] : d0[DH] + d0[DH + 1];
+          }
+          if (lone) {
+            pq = lone_s[0][sp][f];
+            pk = lone_s[1][sp][f];
+            if (from_state) {
+            } else if (pass == 0) {  // rank-1 term of the last key
+#pragma unroll
+              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pk, lone_v[sp][d], sv[d]);
+              zz += pk;
+            } else {  // rank-1 term of the last query
+#pragma unroll
+              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pq, lone_a[sp][d], sv[d]);
+              zz = fmaf(pq, lone_a[sp][DH], zz);
+            }
+          }
+          if (pass == 0) z_s[sp][f] = zz; else dz_s[sp][f] = zz;
+#pragma unroll
+          for (int c = 0; c < DH / 8; ++c) {
+            float ch[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
+            store_split8(simg + (uint32_t)(2 * sp + c) * s_ch, simg + (uint32_t)(4 + 2 * sp + c) * s_ch,
+                         (uint32_t)(f >> 3) * 128 + (f & 7) * 16, ch);
+          }
+        }
+        if (lone) {
+          if (pass == 0) {
+            const float s = warp_sum(pq * zz);  // den of the lone query
+            if (lane == 0) red1_s[warp] = s;
+            fence_smem_to_async();
+            __syncthreads();
+            float den = kEps;
+            for (int w = 8 * sp; w < 8 * sp + 8; ++w) den += red1_s[w];
+            const float r = 1.0f / den;
+            float dot = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dot = fmaf(lone_do[sp][d], lone_o[sp][d], dot);
+            const float a16 = -dot * r;
+            float dph = a16 * zz;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dph = fmaf(lone_do[sp][d] * r, sv[d], dph);
+            const float gq = own ? (favor ? dph * pq : (pq > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
+            const float* wr = w32 + (own ? f : 0) * RW;
+            float a32[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a32[j] = (j <= DH) ? gq * wr[j] : 0.f;
+            const float t = warp_sum32(a32);  // lane j: warp total of partial j
+            if (lane <= DH) red2_s[warp][lane] = t;
+            if ((tid & 255) == 0) {
+#pragma unroll
+              for (int d = 0; d < DH; ++d) lone_a[sp][d] = lone_do[sp][d] * r;
+              lone_a[sp][DH] = a16;
+            }
+          } else {
+            float dph = zz;  // dphi of the lone key: v_L . dS[f] + dz[f]
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dph = fmaf(lone_v[sp][d], sv[d], dph);
+            const float gk = own ? (favor ? dph * pk : (pk > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
+            const float* wr = w32 + (own ? f : 0) * RW;
+            float a32[32];  // [0, DH): dv of the lone key, [DH, 2 DH): G [W^T] ; the row sum goes separately
+#pragma unroll
+            for (int d = 0; d < DH; ++d) {
+              a32[d] = pk * sv[d];
+              a32[DH + d] = gk * wr[d];
+            }
+            const float t = warp_sum32(a32);
+            red3_s[warp][lane] = t;
+            const float t2 = warp_sum(gk * wr[DH]);
+            if (lane == 0) red3_s[warp][2 * DH] = t2;
+          }
+        }
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+      };
+      if (skip) {  // the forward saved [S|z]: fetch this thread's feature row and go straight to the end of the sweep
+        prefetch(g, 1);
+        float st[DH + 1];
+#pragma unroll
+        for (int d = 0; d <= DH; ++d) st[d] = 0.f;
+        {
+          const int sp = part >> 1, hb = part & 1, bb = 2 * b2 + sp;
+          if (hb < nrb && row < HF && bb < B) {
+            const float* src = p.state + ((size_t)bb * H + h) * (DH + 1) * Mp + hb * HF + row;
+#pragma unroll
+            for (int d = 0; d <= DH; ++d) st[d] = __ldg(src + (size_t)d * Mp);
+          }
+        }
+        sweep_tail(true, st);
+      } else {
       // ---- G1: P = x W^T (3xTF32)
       if (tid == 0) {
         fence_after_sync();
@@ -688,93 +804,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         fence_before_sync();
         __syncthreads();  // red (feature images) and the TMEM columns are reused by the next group
       }
-      // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images; lone-token terms
-      if (pass < 2) {
-        const int sp = part >> 1, hb = part & 1, f = hb * HF + row;
-        const bool own = hb < nrb && row < HF;  // warp-uniform
-        float sv[DH], zz = 0.f;
-#pragma unroll
-        for (int d = 0; d < DH; ++d) sv[d] = 0.f;
-        float pq = 0.f, pk = 0.f;
-        if (own) {
-          float d0[32], d1[16];
-          tmem_ld32(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE, d0);
-          tmem_ld16(tm + lane_off + COL_S + (uint32_t)(sp * nrb + hb) * S_STRIDE + 32, d1);
-#pragma unroll
-          for (int d = 0; d < DH; ++d) sv[d] = d0[d] + d1[d];
-          zz = (pass == 0) ? d0[DH] : d0[DH] + d0[DH + 1];
-          if (lone) {
-            pq = lone_s[0][sp][f];
-            pk = lone_s[1][sp][f];
-            if (pass == 0) {  // rank-1 term of the last key
-#pragma unroll
-              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pk, lone_v[sp][d], sv[d]);
-              zz += pk;
-            } else {  // rank-1 term of the last query
-#pragma unroll
-              for (int d = 0; d < DH; ++d) sv[d] = fmaf(pq, lone_a[sp][d], sv[d]);
-              zz = fmaf(pq, lone_a[sp][DH], zz);
-            }
-          }
-          if (pass == 0) z_s[sp][f] = zz; else dz_s[sp][f] = zz;
-#pragma unroll
-          for (int c = 0; c < DH / 8; ++c) {
-            float ch[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
-            store_split8(simg + (uint32_t)(2 * sp + c) * s_ch, simg + (uint32_t)(4 + 2 * sp + c) * s_ch,
-                         (uint32_t)(f >> 3) * 128 + (f & 7) * 16, ch);
-          }
+        if (pass < 2) {
+          const float none[DH + 1] = {};
+          sweep_tail(false, none);
         }
-        if (lone) {
-          if (pass == 0) {
-            const float s = warp_sum(pq * zz);  // den of the lone query
-            if (lane == 0) red1_s[warp] = s;
-            fence_smem_to_async();
-            __syncthreads();
-            float den = kEps;
-            for (int w = 8 * sp; w < 8 * sp + 8; ++w) den += red1_s[w];
-            const float r = 1.0f / den;
-            float dot = 0.f;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) dot = fmaf(lone_do[sp][d], lone_o[sp][d], dot);
-            const float a16 = -dot * r;
-            float dph = a16 * zz;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) dph = fmaf(lone_do[sp][d] * r, sv[d], dph);
-            const float gq = own ? (favor ? dph * pq : (pq > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
-            const float* wr = w32 + (own ? f : 0) * RW;
-#pragma unroll
-            for (int j = 0; j <= DH; ++j) {
-              const float t = warp_sum(gq * wr[j]);
-              if (lane == 0) red2_s[warp][j] = t;
-            }
-            if ((tid & 255) == 0) {
-#pragma unroll
-              for (int d = 0; d < DH; ++d) lone_a[sp][d] = lone_do[sp][d] * r;
-              lone_a[sp][DH] = a16;
-            }
-          } else {
-            float dph = zz;  // dphi of the lone key: v_L . dS[f] + dz[f]
-#pragma unroll
-            for (int d = 0; d < DH; ++d) dph = fmaf(lone_v[sp][d], sv[d], dph);
-            const float gk = own ? (favor ? dph * pk : (pk > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
-            const float* wr = w32 + (own ? f : 0) * RW;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) {
-              const float t = warp_sum(pk * sv[d]);
-              if (lane == 0) red3_s[warp][d] = t;
-            }
-#pragma unroll
-            for (int j = 0; j <= DH; ++j) {
-              const float t = warp_sum(gk * wr[j]);
-              if (lane == 0) red3_s[warp][DH + j] = t;
-            }
-          }
-        }
-        fence_smem_to_async();
-        fence_before_sync();
-        __syncthreads();
       }
     }
   }
@@ -794,10 +827,10 @@ size_t la_tc2_bwd_smem_bytes(int M) {
 
 int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
-                    int dtype, cudaStream_t st) {
+                    int dtype, const float* state, cudaStream_t st) {
   LaTc2BwdArgs a;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.omega = omega; a.ta = ta; a.tb = tb; a.dg_part = dg_part;
-  a.B = B; a.N = N; a.H = H; a.M = M; a.kind = kind; a.rot = rot; a.slots = slots;
+  a.B = B; a.N = N; a.H = H; a.M = M; a.kind = kind; a.rot = rot; a.slots = slots; a.state = state;
   a.prescale = (float)pow(16.0, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
   const int Mp = tc2b_mp(M);

@@ -17,6 +17,7 @@ struct LaTcArgs {
   const float* tb;
   int B, N, H, M, Mp16, kind, rot;
   float prescale, inv_sqrt_m;
+  float* state;  // optional [B*H][DH+1][Mp]: the finished [S|z] of every pair, saved for the backward (short-sequence kernel)
 };
 
 template <int DH>
@@ -118,6 +119,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // contiguous bytes per group of 8 tokens:  byte(t, f) = (f/8)*CH + (t/8)*128 + (t%8)*16 + (f%8)*2.
 // Read as an MN-major operand (rows f, K = t): SBO = CH, LBO = 128; as a K-major operand (rows t, K = f): SBO = 128,
 // LBO = CH.  The same image therefore feeds phi^T [v|1] and phi [S|z].
+// Sums of 32 per-lane values over the warp in 31 shuffles (a plain butterfly per value needs 160): each step halves the
+// values a lane still carries.  Afterwards lane l holds, in the return value, the warp total of the value with index l.
+__device__ __forceinline__ float warp_sum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
 constexpr uint32_t kTokCh = 16 * 128;  // chunk stride of images with 128 token rows
 constexpr int kTcThreads = 512;        // 4 threads per token row, each owns a quarter of the features
 

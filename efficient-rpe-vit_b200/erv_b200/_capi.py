@@ -36,8 +36,9 @@ SIGNATURES = {
     "erv_kerple_attention_workspace": (c_size_t, [_I, _I, _I, _I, _I, _I]),
     "erv_softmax_attention_workspace": (c_size_t, [_I, _I, _I, _I, _I, _I]),
     "erv_circulant_slots": (c_int, [_I, _I]),
-    "erv_linear_attention_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
-    "erv_linear_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _Z, _P]),
+    "erv_linear_attention_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _Z, _P]),
+    "erv_linear_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _Z, _P]),
+    "erv_linear_attention_state_floats": (c_size_t, [_I, _I, _I, _I, _I]),
     "erv_kerple_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_kerple_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_softmax_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, c_uint64, _I, _P, _Z, _P]),

@@ -171,6 +171,9 @@ def feature_map(x, omega, kind):
     return _FeatureMap.apply(x, omega, kind)
 
 
+SAVE_KV_STATE = True  # False: the backward rebuilds [S|z] itself (no extra saved tensor)
+
+
 # ---- attention cores -----------------------------------------------------------------------------------
 class _LinearAttention(torch.autograd.Function):
     @staticmethod
@@ -188,18 +191,22 @@ class _LinearAttention(torch.autograd.Function):
         out = torch.empty(b, n, heads * dh, device=qkv.device, dtype=qkv.dtype)
         nbytes = lib.erv_linear_attention_workspace(b, n, heads, dh, m, rot, 0)
         ws = C.workspace(nbytes, qkv.device)
+        # [phi(k)^T v | sum phi(k)] per (batch, head): written by the forward when a backward will follow
+        nstate = lib.erv_linear_attention_state_floats(b, n, heads, dh, m) if (ctx.needs_input_grad[0] and SAVE_KV_STATE) else 0
+        state = torch.empty(nstate, device=qkv.device, dtype=torch.float32) if nstate else None
         with _timed("linear_attention_fwd"):
             C.check(lib.erv_linear_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(omega), b, n, heads, dh, m, kind, rot,
-                                                 C.ptr(ta), C.ptr(tb), C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                                                 C.ptr(ta), C.ptr(tb), C.dtype_code(qkv), C.ptr(state), C.ptr(ws), nbytes,
+                                                 C.stream()),
                     "linear_attention")
         ctx.meta = (b, n, heads, dh, m, kind, rot)
-        ctx.save_for_backward(qkv, out, omega, ta, tb)
+        ctx.save_for_backward(qkv, out, omega, ta, tb, state)
         return out
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        qkv, out, omega, ta, tb = ctx.saved_tensors
+        qkv, out, omega, ta, tb, state = ctx.saved_tensors
         b, n, heads, dh, m, kind, rot = ctx.meta
         lib = C.load()
         dout = dout.to(qkv.dtype).contiguous()
@@ -213,7 +220,7 @@ class _LinearAttention(torch.autograd.Function):
         with _timed("linear_attention_bwd"):
             C.check(lib.erv_linear_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(dout), C.ptr(dqkv), C.ptr(omega), b, n, heads,
                                                  dh, m, kind, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), C.dtype_code(qkv),
-                                                 C.ptr(ws), nbytes, C.stream()), "linear_attention_bwd")
+                                                 C.ptr(state), C.ptr(ws), nbytes, C.stream()), "linear_attention_bwd")
         dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[2]) else None
         return dqkv, None, dgtab, None, None, None, None, None
 

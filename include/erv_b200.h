@@ -99,14 +99,19 @@ int erv_circulant_slots(int B, int H);
  * omega [H, Dh, M].  rot tables as in erv_rotate (rope tables cover positions 0..N-1). */
 int erv_linear_attention_fwd(const void* qkv, void* out, const float* omega, int B, int N, int H,
                              int head_dim, int M, int kind, int rot, const float* tab_a,
-                             const float* tab_b, int dtype, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             const float* tab_b, int dtype, float* kv_state, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* Floats of the optional kv_state buffer: the finished [phi(k)^T v | sum_n phi(k)] of every (batch, head)
+ * pair, which the forward writes and the backward reads instead of rebuilding it (the reference's autograd
+ * saves the same tensors, favor_plus.py:250-257).  0 = these shapes do not use it; pass NULL then.  Passing
+ * NULL to both calls is always valid (the backward recomputes). */
+size_t erv_linear_attention_state_floats(int B, int N, int H, int head_dim, int M);
 /* Backward (replaces autograd over the ops above).  `out` is the saved forward
  * output.  dg_part ([H, erv_circulant_slots, N, Dh], circulant only) is overwritten. */
 int erv_linear_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv,
                              const float* omega, int B, int N, int H, int head_dim, int M, int kind,
                              int rot, const float* tab_a, const float* tab_b, float* dg_part, int dtype,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             const float* kv_state, void* workspace, size_t workspace_bytes, void* stream);
 
 /* KERPLE linear attention (favor_plus.py:197-245 + kerple.py:99-344 + fft_utils.py:112-172), evaluated
  * as Toeplitz-masked attention: A = (phi(q) phi(k)^T) * exp(bias[j-i+N-1]); out = A v / (A 1 + 1e-6)

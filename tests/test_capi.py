@@ -39,7 +39,7 @@ def test_status_to_exception_mapping():
         _capi.check(_capi.E_INVALID, "x")
     with pytest.raises(NotImplementedError):
         _capi.check(_capi.E_UNSUPPORTED, "x")
-    assert lib.erv_linear_attention_fwd(None, None, None, 1, 1, 1, 12, 4, 0, 0, None, None, 0, None, 0, None) == _capi.E_UNSUPPORTED
+    assert lib.erv_linear_attention_fwd(None, None, None, 1, 1, 1, 12, 4, 0, 0, None, None, 0, None, None, 0, None) == _capi.E_UNSUPPORTED
     assert b"head_dim" in lib.erv_last_error()
     assert lib.erv_circulant_slots(1024, 2) >= 1
     assert lib.erv_linear_attention_workspace(8, 65, 2, 16, 256, 0, 1) > 0

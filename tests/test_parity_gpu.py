@@ -176,6 +176,22 @@ def test_attention_matches_oracle(a, r, b, n, dim, heads, m):
             assert rel_l2(p.grad, l.grad) < TOL_F32
 
 
+def test_linear_backward_without_saved_state(monkeypatch):
+    """The short-sequence backward gives the same gradients whether it reads the forward's saved [S|z] or rebuilds it."""
+    from erv_b200 import FAVORPlusAttention, ops
+    torch.manual_seed(5)
+    attn = FAVORPlusAttention(32, 2, num_features=256).to(DEV)
+    qkv = torch.randn(7, 65, 96, device=DEV)
+    w = torch.randn(7, 65, 32, device=DEV)
+    grads = []
+    for save in (True, False):
+        monkeypatch.setattr(ops, "SAVE_KV_STATE", save)
+        q = qkv.clone().requires_grad_(True)
+        (ops.linear_attention(q, attn.omega, 2, ops.FEAT_FAVOR) * w).sum().backward()
+        grads.append(q.grad)
+    assert rel_l2(grads[0], grads[1]) < 1e-5
+
+
 def test_softmax_mask_and_return_attention():
     from erv_b200 import SoftmaxAttention
     from oracle import erv_oracle as O
