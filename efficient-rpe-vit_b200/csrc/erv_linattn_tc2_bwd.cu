@@ -31,7 +31,10 @@ struct LaTc2BwdArgs {
   const float* state;  // optional [B*H][DH+1][Mp]: [S|z] saved by the forward; the K1 sweep is skipped when present
   int B, N, H, M, kind, rot, slots;
   float prescale, inv_sqrt_m;
+  long long* trace;  // optional: CTA 0 / thread 0 stamps clock64() at phase boundaries (erv_debug_set_trace)
 };
+
+extern long long* g_trace;
 
 // raw 16-element row held as loaded (conversion to fp32 is deferred so the load stays in flight)
 template <typename T> struct RawRow;
@@ -191,6 +194,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   const uint32_t tm = tmem_base_s;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t ph_a = 0, ph_b = 0, ph_c = 0;
+  int tr_i = 0;
+  auto TR = [&](int tag) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && tr_i < 1000) {
+      p.trace[2 * tr_i] = tag;
+      p.trace[2 * tr_i + 1] = clock64();
+      ++tr_i;
+    }
+  };
 
   const T* qkv = static_cast<const T*>(p.qkv);
   const T* outp = static_cast<const T*>(p.out);
@@ -253,6 +264,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
       for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
       const bool skip = pass == 0 && have_state;  // S comes from the forward: no K1 sweep
+      float st[DH + 1];  // skip: this thread's feature row of the saved [S|z], in flight across the first barrier
+#pragma unroll
+      for (int d = 0; d <= DH; ++d) st[d] = 0.f;
+      if (skip) {
+        const int sp = part >> 1, hb = part & 1, bb = 2 * b2 + sp;
+        if (hb < nrb && row < HF && bb < B) {
+          const float* src = p.state + ((size_t)bb * H + h) * (DH + 1) * Mp + hb * HF + row;
+#pragma unroll
+          for (int d = 0; d <= DH; ++d) st[d] = __ldg(src + (size_t)d * Mp);
+        }
+      }
+      TR(pass * 100 + 0);
       if (skip) {
         // only the lone-token rows (part 3 below) are prepared
       } else if (part == 0) {
@@ -308,13 +331,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
           const int f = lane + 32 * i;
-          const float* wr = w32 + f * RW;
+          const uint32_t wo = (uint32_t)(f >> 3) * C::X_SBO + (f & 7) * 16;  // TF32 images: conflict-free 16-byte reads
           float acc = 0.f;
 #pragma unroll
           for (int c = 0; c < DH / 4; ++c) {
-            const float4 a = ld4(wr + 4 * c);
-            acc = fmaf(x[4 * c], a.x, acc); acc = fmaf(x[4 * c + 1], a.y, acc);
-            acc = fmaf(x[4 * c + 2], a.z, acc); acc = fmaf(x[4 * c + 3], a.w, acc);
+            const float4 a = ld4(reinterpret_cast<const float*>(wh + wo + c * C::X_LBO));
+            const float4 l = ld4(reinterpret_cast<const float*>(wl + wo + c * C::X_LBO));
+            acc = fmaf(x[4 * c], a.x + l.x, acc); acc = fmaf(x[4 * c + 1], a.y + l.y, acc);
+            acc = fmaf(x[4 * c + 2], a.z + l.z, acc); acc = fmaf(x[4 * c + 3], a.w + l.w, acc);
           }
           pv[i] = acc;
           if (f < M) m = fmaxf(m, acc);
@@ -387,6 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       }
       // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images; lone-token terms
       auto sweep_tail = [&](const bool from_state, const float (&st)[DH + 1]) {
+        TR(pass * 100 + 20);
         const int sp = part >> 1, hb = part & 1, f = hb * HF + row;
         const bool own = hb < nrb && row < HF;  // warp-uniform
         float sv[DH], zz = 0.f;
@@ -482,19 +507,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       };
       if (skip) {  // the forward saved [S|z]: fetch this thread's feature row and go straight to the end of the sweep
         prefetch(g, 1);
-        float st[DH + 1];
-#pragma unroll
-        for (int d = 0; d <= DH; ++d) st[d] = 0.f;
-        {
-          const int sp = part >> 1, hb = part & 1, bb = 2 * b2 + sp;
-          if (hb < nrb && row < HF && bb < B) {
-            const float* src = p.state + ((size_t)bb * H + h) * (DH + 1) * Mp + hb * HF + row;
-#pragma unroll
-            for (int d = 0; d <= DH; ++d) st[d] = __ldg(src + (size_t)d * Mp);
-          }
-        }
         sweep_tail(true, st);
       } else {
+      TR(pass * 100 + 1);
       // ---- G1: P = x W^T (3xTF32)
       if (tid == 0) {
         fence_after_sync();
@@ -515,6 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       mbar_wait(&bar_a, ph_a);
       ph_a ^= 1;
       fence_after_sync();
+      TR(pass * 100 + 2);
       // ---- P -> registers, row max, phi (kept in pr as fp32 bit patterns)
       uint32_t pr[NC][8];
 #pragma unroll
@@ -563,6 +579,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           }
         }
       }
+      TR(pass * 100 + 3);
       // stores one feature half of the values held in pr into the phi images
       auto store_half = [&](int hb) {
 #pragma unroll
@@ -607,8 +624,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       };
       // G (in pr) x [W^T | 1]: this thread's partial sums
       auto gradient_partial = [&](float (&acc)[RW]) {
+        unsigned long long a2[RW / 2];  // packed pairs: FFMA2 halves the issue slots of this FMA-bound loop
 #pragma unroll
-        for (int j = 0; j < RW; ++j) acc[j] = 0.f;
+        for (int j = 0; j < RW / 2; ++j) a2[j] = 0ull;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int f0 = feat0(c);
@@ -619,12 +637,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
             for (int cd = 0; cd < RW / 4; ++cd) {
               const float4 a = ld4(wr + 4 * cd);
-              acc[4 * cd] = fmaf(gq, a.x, acc[4 * cd]);
-              acc[4 * cd + 1] = fmaf(gq, a.y, acc[4 * cd + 1]);
-              acc[4 * cd + 2] = fmaf(gq, a.z, acc[4 * cd + 2]);
-              acc[4 * cd + 3] = fmaf(gq, a.w, acc[4 * cd + 3]);
+              ffma2(a2[2 * cd], gq, a.x, a.y);
+              ffma2(a2[2 * cd + 1], gq, a.z, a.w);
             }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < RW / 2; ++j) {
+          acc[2 * j] = lo_of(a2[j]);
+          acc[2 * j + 1] = hi_of(a2[j]);
         }
       };
       // reduced sums (part 0) -> gradient wrt the raw q/k row, written to global memory
@@ -689,6 +710,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         den_s[part][row] = den_part;
         store_half(0);  // does not depend on den: overlaps the exchange
         __syncthreads();
+        TR(104);
         if (part == 1) {
           const float r = 1.0f / ((den_s[0][row] + den_s[1][row]) + (den_s[2][row] + den_s[3][row]) + kEps);
           float dot = 0.f;
@@ -726,9 +748,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             }
           commit(&bar_c);
         }
+        TR(105);
         mbar_wait(&bar_b, ph_b);
         ph_b ^= 1;
         fence_after_sync();
+        TR(106);
         if (nrb > 1) {
           store_half(1);
           fence_smem_to_async();
@@ -739,21 +763,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             issue_accumulate(1);
           }
         }
+        TR(107);
         mbar_wait(&bar_c, ph_c);
         ph_c ^= 1;
         fence_after_sync();
+        TR(108);
         load_dphi_to_g(&z_s[side][0], a16_s[row]);
         fence_before_sync();
+        TR(109);
         float acc[RW];
         gradient_partial(acc);
+        TR(110);
         if (nrb > 1) {
           mbar_wait(&bar_b, ph_b);  // the second half's contraction has read the feature images: red may alias them
           ph_b ^= 1;
           fence_after_sync();
         }
         reduce_rows(acc);
+        TR(111);
         store_input_gradient(acc);
         prefetch(g, 2);
+        TR(112);
       } else {
         // ---- K2: dv = phi_k [dS_A|dS_B] ; dphi_k (already issued) ; dk
         for (int hb = 0; hb < nrb; ++hb) {
@@ -776,18 +806,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             fence_after_sync();
           }
         }
+        TR(207);
         mbar_wait(&bar_c, ph_c);
         ph_c ^= 1;
         fence_after_sync();
+        TR(208);
         load_dphi_to_g(&dz_s[side][0], 1.0f);
         fence_before_sync();
+        TR(209);
         float acc[RW];
         gradient_partial(acc);
+        TR(210);
         mbar_wait(&bar_b, ph_b);
         ph_b ^= 1;
         fence_after_sync();
         reduce_rows(acc);
+        TR(211);
         store_input_gradient(acc);
+        TR(212);
         prefetch(g + gridDim.x, 0);
         if (part == 0) {  // dv rows: hi-part + lo-part columns of this row's pair
           float a0[16], a1[16];
@@ -803,6 +839,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         }
         fence_before_sync();
         __syncthreads();  // red (feature images) and the TMEM columns are reused by the next group
+        TR(213);
       }
         if (pass < 2) {
           const float none[DH + 1] = {};
@@ -831,6 +868,7 @@ int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dq
   LaTc2BwdArgs a;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.omega = omega; a.ta = ta; a.tb = tb; a.dg_part = dg_part;
   a.B = B; a.N = N; a.H = H; a.M = M; a.kind = kind; a.rot = rot; a.slots = slots; a.state = state;
+  a.trace = g_trace;
   a.prescale = (float)pow(16.0, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
   const int Mp = tc2b_mp(M);

@@ -30,7 +30,7 @@ struct LaTcBwdArgs {
   long long* trace;  // optional: CTA 0 / thread 0 stamps clock64() at phase boundaries (erv_debug_set_trace)
 };
 
-static long long* g_trace = nullptr;
+long long* g_trace = nullptr;  // erv_debug_set_trace(); also read by erv_linattn_tc2_bwd.cu
 
 __device__ __forceinline__ void unpack8(const uint8_t* hi_img, const uint8_t* lo_img, uint32_t off, float (&v)[8]) {
   const uint4 h = *reinterpret_cast<const uint4*>(hi_img + off);

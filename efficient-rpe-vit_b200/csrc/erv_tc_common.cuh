@@ -136,6 +136,16 @@ __device__ __forceinline__ float warp_sum32(float (&v)[32]) {
   return v[0];
 }
 
+// packed fp32 pair FMA (FFMA2 on sm_100): acc.{lo,hi} += g * w.{lo,hi}; one issue slot for two FMAs
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, float g, float w_lo, float w_hi) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(g, g)), "l"(pack2(w_lo, w_hi)));
+}
+__device__ __forceinline__ float lo_of(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
 constexpr uint32_t kTokCh = 16 * 128;  // chunk stride of images with 128 token rows
 constexpr int kTcThreads = 512;        // 4 threads per token row, each owns a quarter of the features
 
