@@ -5,7 +5,7 @@ raises.  The library is built in-tree by ``efficient-rpe-vit_b200/csrc/build.py`
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p  # noqa: F401
 
 import torch
 
@@ -39,6 +39,15 @@ SIGNATURES = {
     "erv_linear_attention_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _Z, _P]),
     "erv_linear_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _Z, _P]),
     "erv_linear_attention_state_floats": (c_size_t, [_I, _I, _I, _I, _I]),
+    "erv_block_supported": (c_int, [_I, _I]),
+    "erv_block_ln_qkv_params": (c_int, []),
+    "erv_block_mlp_params": (c_int, []),
+    "erv_block_ln_qkv_bwd_workspace": (c_size_t, [_I]),
+    "erv_block_mlp_bwd_workspace": (c_size_t, [_I]),
+    "erv_block_ln_qkv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "erv_block_ln_qkv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _Z, _P]),
+    "erv_block_mlp_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P]),
+    "erv_block_mlp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P, _Z, _P]),
     "erv_kerple_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_kerple_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_softmax_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, c_uint64, _I, _P, _Z, _P]),

@@ -57,20 +57,26 @@ class RandomFeatureAttention(BaseAttention):
     def _features(self, x: torch.Tensor, omega: torch.Tensor) -> torch.Tensor:
         return ops.feature_map(x, omega, self._kind)
 
-    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,
-                return_attention: bool = False) -> torch.Tensor:
+    def before_qkv(self, x_shape, rpe):
+        """Per-call bookkeeping that precedes the qkv projection: feature redraw, RPE shape checks."""
         if self.training and self.feature_redraw_interval is not None:  # favor_plus.py:168-171
             if int(self.redraw_counter) % self.feature_redraw_interval == 0:
                 self._create_random_features()
             self.redraw_counter += 1
         if isinstance(rpe, KERPLEPositionalEncoding):
-            rpe._check(self.heads, x.shape[1])
-            qkv = self.qkv(x)
-            out = ops.kerple_attention(qkv, self.omega, rpe.rel_pos_bias, self.heads, self._kind)
-        else:
-            rot, gtab, ta, tb = rotation_args(rpe, x.shape, self.heads, self.head_dim)
-            qkv = self.qkv(x)
-            out = ops.linear_attention(qkv, self.omega, self.heads, self._kind, rot, gtab, ta, tb)
+            rpe._check(self.heads, x_shape[1])
+
+    def core(self, qkv: torch.Tensor, x_shape, rpe: Optional[nn.Module] = None) -> torch.Tensor:
+        """Packed qkv [B, N, 3C] -> attention output [B, N, C] before the output projection."""
+        if isinstance(rpe, KERPLEPositionalEncoding):
+            return ops.kerple_attention(qkv, self.omega, rpe.rel_pos_bias, self.heads, self._kind)
+        rot, gtab, ta, tb = rotation_args(rpe, x_shape, self.heads, self.head_dim)
+        return ops.linear_attention(qkv, self.omega, self.heads, self._kind, rot, gtab, ta, tb)
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,
+                return_attention: bool = False) -> torch.Tensor:
+        self.before_qkv(x.shape, rpe)
+        out = self.core(self.qkv(x), x.shape, rpe)
         out = self.proj_dropout(self.proj(out))
         if return_attention:  # favor_plus.py:267-273: raised after the work, as in the reference
             raise NotImplementedError(

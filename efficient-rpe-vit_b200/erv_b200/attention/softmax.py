@@ -19,18 +19,26 @@ class SoftmaxAttention(BaseAttention):
         self.attn_dropout = nn.Dropout(dropout)  # kept for module-tree parity; the kernel applies it
         self.proj_dropout = nn.Dropout(dropout)
 
-    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,
-                return_attention: bool = False):
+    def before_qkv(self, x_shape, rpe):
         if isinstance(rpe, KERPLEPositionalEncoding):  # softmax.py:69-77
             raise NotImplementedError(
                 "KERPLE RPE is designed specifically for kernelized attention (FAVOR+/ReLU Performer) and "
                 "cannot be used with standard softmax attention. For softmax attention, use RoPE or "
                 "Circulant-STRING RPE instead.")
-        rot, gtab, ta, tb = rotation_args(rpe, x.shape, self.heads, self.head_dim)
-        qkv = self.qkv(x)
+
+    def core(self, qkv: torch.Tensor, x_shape, rpe: Optional[nn.Module] = None, mask=None, return_attention: bool = False):
+        """Packed qkv [B, N, 3C] -> attention output [B, N, C] before the output projection (and the weights)."""
+        rot, gtab, ta, tb = rotation_args(rpe, x_shape, self.heads, self.head_dim)
         p = self.attn_dropout.p if self.training else 0.0
         out, attn = ops.softmax_attention(qkv, self.heads, rot, gtab, ta, tb, mask, p,
                                           ops.next_seed() if p > 0 else 0, return_attention)
+        return (out, attn) if return_attention else out
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,
+                return_attention: bool = False):
+        self.before_qkv(x.shape, rpe)
+        res = self.core(self.qkv(x), x.shape, rpe, mask, return_attention)
+        out, attn = res if return_attention else (res, None)
         out = self.proj_dropout(self.proj(out))
         return (out, attn) if return_attention else out
 

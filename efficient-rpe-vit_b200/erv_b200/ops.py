@@ -444,6 +444,112 @@ class _LayerNorm(torch.autograd.Function):
         return dx.reshape(ctx.shape), dg, db, None
 
 
+# ---- fused block kernels (dim 32, MLP width 64): LayerNorm1 + qkv ; proj + residual + LayerNorm2 + MLP + residual ------
+FUSED_BLOCK = True  # False: the block runs op by op (Linear / LayerNorm / GELU / Dropout modules)
+
+_drop_state = {}
+
+
+def dropout_seed(device):
+    """A fresh device-resident dropout seed (int64 scalar): a per-device counter that lives on the GPU, so the value
+    changes on every CUDA-graph replay.  Initialised from torch's seed and the data-parallel rank."""
+    st = _drop_state.get(device)
+    if st is None:
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        st = torch.tensor([(torch.initial_seed() * 0x9E3779B1 + rank * 0x632BE5AB) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
+                          device=device)
+        _drop_state[device] = st
+    seed = st.clone()
+    st.add_(0x2545F491)
+    return seed
+
+
+class _BlockLnQkv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b, eps):
+        C.require_cuda(x, ln_w, ln_b, w)
+        dim = x.shape[-1]
+        x2 = x.reshape(-1, dim).contiguous()
+        rows = x2.shape[0]
+        qkv = torch.empty(rows, 3 * dim, device=x.device, dtype=torch.float32)
+        C.check(C.load().erv_block_ln_qkv_fwd(C.ptr(x2), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(qkv), rows, dim,
+                                              float(eps), C.stream()), "block_ln_qkv")
+        ctx.save_for_backward(x2, ln_w, ln_b, w)
+        ctx.meta = (x.shape, float(eps), b is not None)
+        return qkv.reshape(*x.shape[:-1], 3 * dim)
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        x2, ln_w, ln_b, w = ctx.saved_tensors
+        shape, eps, has_bias = ctx.meta
+        rows, dim = x2.shape
+        lib = C.load()
+        dq = dqkv.reshape(rows, 3 * dim).to(torch.float32).contiguous()
+        dx = torch.empty_like(x2)
+        dpar = torch.empty(lib.erv_block_ln_qkv_params(), device=x2.device, dtype=torch.float32)
+        nbytes = lib.erv_block_ln_qkv_bwd_workspace(rows)
+        ws = C.workspace(nbytes, x2.device)
+        C.check(lib.erv_block_ln_qkv_bwd(C.ptr(x2), C.ptr(dq), None, C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(dx), C.ptr(dpar),
+                                         rows, dim, eps, C.ptr(ws), nbytes, C.stream()), "block_ln_qkv_bwd")
+        nw = 3 * dim * dim
+        dw = dpar[:nw].view(3 * dim, dim)
+        db = dpar[nw:nw + 3 * dim] if has_bias else None
+        return dx.reshape(shape), dpar[nw + 3 * dim:nw + 4 * dim], dpar[nw + 4 * dim:nw + 5 * dim], dw, db, None
+
+
+def block_supported(dim: int, mlp_dim: int) -> bool:
+    return bool(C.load().erv_block_supported(int(dim), int(mlp_dim)))
+
+
+def block_ln_qkv(x, ln_w, ln_b, w, b, eps=1e-5):
+    return _BlockLnQkv.apply(x, ln_w, ln_b, w, b, eps)
+
+
+def _param_array(params):
+    return (C.c_void_p * len(params))(*[t.data_ptr() for t in params])
+
+
+class _BlockMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps, p_drop, seed, salt):
+        C.require_cuda(a, x, wp)
+        dim, mlp_dim = x.shape[-1], w1.shape[0]
+        a2 = a.reshape(-1, dim).to(torch.float32).contiguous()
+        x2 = x.reshape(-1, dim).contiguous()
+        rows = x2.shape[0]
+        params = (wp, bp, ln_w, ln_b, w1, b1, w2, b2)
+        y = torch.empty_like(x2)
+        C.check(C.load().erv_block_mlp_fwd(C.ptr(a2), C.ptr(x2), _param_array(params), C.ptr(y), rows, dim, mlp_dim, float(eps),
+                                           float(p_drop), C.ptr(seed), int(salt), C.stream()), "block_mlp")
+        ctx.save_for_backward(a2, x2, seed, *params)
+        ctx.meta = (x.shape, float(eps), float(p_drop), int(salt), mlp_dim)
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a2, x2, seed, *params = ctx.saved_tensors
+        shape, eps, p_drop, salt, mlp_dim = ctx.meta
+        rows, dim = x2.shape
+        lib = C.load()
+        dy2 = dy.reshape(rows, dim).to(torch.float32).contiguous()
+        da, dx1 = torch.empty_like(a2), torch.empty_like(x2)
+        dpar = torch.empty(lib.erv_block_mlp_params(), device=x2.device, dtype=torch.float32)
+        nbytes = lib.erv_block_mlp_bwd_workspace(rows)
+        ws = C.workspace(nbytes, x2.device)
+        C.check(lib.erv_block_mlp_bwd(C.ptr(a2), C.ptr(x2), C.ptr(dy2), _param_array(params), C.ptr(da), C.ptr(dx1), C.ptr(dpar),
+                                      rows, dim, mlp_dim, eps, p_drop, C.ptr(seed), salt, C.ptr(ws), nbytes, C.stream()),
+                "block_mlp_bwd")
+        o, grads = 0, []
+        for t in params:  # dparams follows the parameter order
+            grads.append(dpar[o:o + t.numel()].view(t.shape))
+            o += t.numel()
+        return (da.reshape(shape), dx1.reshape(shape), *grads, None, None, None, None)
+
+
+def block_mlp(a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, p_drop=0.0, seed=None, salt=0):
+    return _BlockMlp.apply(a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps, p_drop, seed, salt)
+
+
 def layer_norm(x, weight, bias, eps=1e-5):
     if (not x.is_cuda) or x.shape[-1] > 256 or weight is None or bias is None or weight.dtype != torch.float32:
         return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)

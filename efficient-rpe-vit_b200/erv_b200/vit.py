@@ -9,6 +9,7 @@ from typing import Callable, Dict, Optional
 import torch
 import torch.nn as nn
 
+from . import ops
 from .nn import LayerNorm, Linear
 
 
@@ -28,8 +29,31 @@ class UnifiedTransformerBlock(nn.Module):
         self.norm2 = LayerNorm(dim)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fused(x):
+            return self._forward_fused(x)
         x = x + self.attention(self.norm1(x), rpe=self.rpe)  # the RPE goes INTO the attention
         return x + self.mlp(self.norm2(x))
+
+    # ---- fused path (csrc/erv_block_fused.cu): two kernels around the attention core instead of ~14 library ops
+    def _fused(self, x: torch.Tensor) -> bool:
+        att = self.attention
+        if not (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled()):
+            return False
+        if not (hasattr(att, "core") and hasattr(att, "qkv") and hasattr(att, "proj") and hasattr(att, "proj_dropout")):
+            return False
+        if att.qkv.weight.dtype != torch.float32 or att.proj.bias is None or not ops.block_supported(self.dim, self.mlp_dim):
+            return False
+        return att.proj_dropout.p == self.mlp[2].p == self.mlp[4].p
+
+    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+        att = self.attention
+        att.before_qkv(x.shape, self.rpe)
+        qkv = ops.block_ln_qkv(x, self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, self.norm1.eps)
+        a = att.core(qkv, x.shape, self.rpe)
+        p = self.mlp[2].p if self.training else 0.0
+        seed = ops.dropout_seed(x.device) if p > 0 else None
+        return ops.block_mlp(a, x, att.proj.weight, att.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp[0].weight,
+                             self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias, self.norm2.eps, p, seed)
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}, mlp_dim={self.mlp_dim}, has_rpe={self.rpe is not None}"

@@ -113,6 +113,39 @@ int erv_linear_attention_bwd(const void* qkv, const void* out, const void* dout,
                              int rot, const float* tab_a, const float* tab_b, float* dg_part, int dtype,
                              const float* kv_state, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the block around the attention core, dim 32 / MLP width 64 only -------- */
+
+/* 1 when the fused block kernels below cover these dims (the reference's: configs/datasets/mnist.py:20-24). */
+int erv_block_supported(int dim, int mlp_dim);
+/* qkv [rows, 3*dim] = LayerNorm(x; ln_w, ln_b, eps) w_qkv^T (+ b_qkv, may be NULL): norm1 + attention.qkv
+ * (unified_transformer.py:75-83, favor_plus.py:174).  fp32, x [rows, dim]. */
+int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,
+                         const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream);
+/* Backward: dx = dres (may be NULL) + d/dx ; dparams [erv_block_ln_qkv_params()] = dW_qkv [3 dim, dim] |
+ * db_qkv [3 dim] | dln_w [dim] | dln_b [dim].  Recomputes the LayerNorm from x. */
+int erv_block_ln_qkv_params(void);
+size_t erv_block_ln_qkv_bwd_workspace(int rows);
+int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, const float* ln_w,
+                         const float* ln_b, const float* w_qkv, float* dx, float* dparams, int rows, int dim,
+                         float eps, void* workspace, size_t workspace_bytes, void* stream);
+/* y = x1 + drop(fc2(drop(gelu(fc1(LayerNorm(x1)))))),  x1 = x + drop(attn_out w_proj^T + b_proj):
+ * attention.proj + proj_dropout + residual + norm2 + mlp + residual (favor_plus.py:263-265,
+ * unified_transformer.py:85-88).  params = {w_proj, b_proj, ln_w, ln_b, w_fc1, b_fc1, w_fc2, b_fc2}
+ * (nn.Linear layouts).  Dropout masks are a counter hash of (*seed, salt, element); seed is a device
+ * pointer (CUDA-graph friendly) and may be NULL when p_drop == 0. */
+int erv_block_mlp_fwd(const float* attn_out, const float* x, const float* const* params, float* y, int rows,
+                      int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt,
+                      void* stream);
+/* Backward: recomputes the forward from (attn_out, x, seed).  d_attn_out, dx1 [rows, dim] (dx1 is the
+ * gradient of the residual stream, i.e. of x); dparams [erv_block_mlp_params()] = dW_proj | db_proj |
+ * dln_w | dln_b | dW_fc1 | db_fc1 | dW_fc2 | db_fc2. */
+int erv_block_mlp_params(void);
+size_t erv_block_mlp_bwd_workspace(int rows);
+int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, const float* const* params,
+                      float* d_attn_out, float* dx1, float* dparams, int rows, int dim, int mlp_dim, float eps,
+                      float p_drop, const long long* seed, int salt, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* KERPLE linear attention (favor_plus.py:197-245 + kerple.py:99-344 + fft_utils.py:112-172), evaluated
  * as Toeplitz-masked attention: A = (phi(q) phi(k)^T) * exp(bias[j-i+N-1]); out = A v / (A 1 + 1e-6)
  * with q, k L2-normalised.  rel_pos_bias [H, 2N-1].  den_out [B, H, N] is saved for the backward. */

@@ -65,3 +65,73 @@ def test_layernorm_matches_torch(r, c):
     assert rel_l2(got[1], x.grad) < 1e-5
     assert rel_l2(got[2], ln.weight.grad) < 1e-5
     assert rel_l2(got[3], ln.bias.grad) < 1e-5
+
+
+# ---- fused block kernels (csrc/erv_block_fused.cu) ---------------------------------------------------------------------
+def _make_block(dropout=0.0):
+    from erv_b200 import FAVORPlusAttention
+    from erv_b200.vit import UnifiedTransformerBlock
+    torch.manual_seed(11)
+    blk = UnifiedTransformerBlock(32, FAVORPlusAttention(32, 2, dropout=dropout, num_features=64), None, 64, dropout)
+    with torch.no_grad():  # non-trivial LayerNorm affine parameters and biases
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.normal_(0.5, 0.3)
+    return blk.to("cuda")
+
+
+@pytest.mark.parametrize("shape", [(3, 65, 32), (1, 5, 32), (16, 197, 32)])
+def test_fused_block_matches_unfused(shape, monkeypatch):
+    """The two fused kernels (+ their backward) against the same block run op by op (library GEMMs, ATen GELU, ...)."""
+    from erv_b200 import ops
+    blk = _make_block().eval()
+    x = torch.randn(*shape, device="cuda")
+    w = torch.randn(*shape, device="cuda")
+    res = []
+    for fused in (True, False):
+        monkeypatch.setattr(ops, "FUSED_BLOCK", fused)
+        blk.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y = blk(xi)
+        (y * w).sum().backward()
+        res.append((y.detach(), xi.grad, {k: p.grad.clone() for k, p in blk.named_parameters()}))
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert rel_l2(y1, y0) < 1e-5 and rel_l2(dx1, dx0) < 2e-5
+    for k in g0:
+        assert rel_l2(g1[k], g0[k]) < 5e-5, k
+
+
+def test_fused_block_dropout_is_consistent():
+    """Training-mode dropout: keep rate, forward/backward use the same masks (directional derivative), and a new
+    seed gives new masks."""
+    from erv_b200 import ops
+    torch.manual_seed(3)
+    a = torch.randn(512, 65, 32, device="cuda")
+    x = torch.zeros(512, 65, 32, device="cuda")
+    eye, zero = torch.eye(32, device="cuda"), torch.zeros(32, device="cuda")
+    ones = torch.ones(32, device="cuda")
+    w1, b1 = torch.zeros(64, 32, device="cuda"), torch.zeros(64, device="cuda")
+    w2 = torch.zeros(32, 64, device="cuda")
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    # identity projection, zero MLP: y = drop(a)
+    y = ops.block_mlp(a, x, eye, zero, ones, zero, w1, b1, w2, zero, 1e-5, 0.25, seed)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.75) < 0.01
+    assert torch.allclose(y[y != 0], (a / 0.75)[y != 0], rtol=1e-5)
+    y2 = ops.block_mlp(a, x, eye, zero, ones, zero, w1, b1, w2, zero, 1e-5, 0.25, seed + 1)
+    assert ((y != 0) != (y2 != 0)).float().mean().item() > 0.2
+    # full block: gradient along a random direction equals the central difference with the masks held fixed
+    blk = _make_block(dropout=0.2).train()
+    att = blk.attention
+    args = lambda t: (t, xin, att.proj.weight, att.proj.bias, blk.norm2.weight, blk.norm2.bias, blk.mlp[0].weight,  # noqa: E731
+                      blk.mlp[0].bias, blk.mlp[3].weight, blk.mlp[3].bias, 1e-5, 0.2, seed)
+    xin = torch.randn(64, 65, 32, device="cuda")
+    a0 = torch.randn(64, 65, 32, device="cuda", dtype=torch.float64).float().requires_grad_(True)
+    v = torch.randn_like(a0)
+    wgt = torch.randn_like(a0)
+    (ops.block_mlp(*args(a0)) * wgt).sum().backward()
+    eps = 1e-2
+    with torch.no_grad():
+        fd = ((ops.block_mlp(*args(a0 + eps * v)) - ops.block_mlp(*args(a0 - eps * v))) * wgt).double().sum() / (2 * eps)
+    an = (a0.grad * v).double().sum()
+    assert abs(float(fd - an)) / abs(float(an)) < 2e-2
