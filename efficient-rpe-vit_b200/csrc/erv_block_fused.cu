@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(THREADS) mlp_fwd_kernel(const MlpArgs p) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS) mlp_bwd_kernel(const MlpArgs p) {
+__global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
   extern __shared__ __align__(16) float sm[];
   float* Wp = sm;                   // proj fwd
   float* W1 = Wp + C * C;           // fc1 fwd
@@ -480,13 +480,52 @@ __global__ void __launch_bounds__(THREADS) mlp_bwd_kernel(const MlpArgs p) {
   }
 }
 
-// out[k] = sum over CTAs of part[cta][k], fixed order
-__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int P) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P) return;
-  float s = 0.f;
-  for (int c = 0; c < n; ++c) s += part[(size_t)c * P + k];
-  out[k] = s;
+// out[k] = sum over CTAs of part[cta][k] in a fixed order: 32 entries per CTA, 8 slices of the partial list per entry.
+// With `dst` (one pointer per parameter segment, segment s = entries [seg[s], seg[s+1])) the sums are ADDED to the
+// parameters' gradient buffers instead (fused gradient accumulation); a null segment pointer is skipped.
+struct SumArgs {
+  const float* part; float* out; int n, P, nseg;
+  float* dst[8]; int seg[9];
+};
+__global__ void __launch_bounds__(256) sum_partials_kernel(const SumArgs a) {
+  __shared__ float sh[8][32];
+  const int kx = threadIdx.x & 31, sl = threadIdx.x >> 5, k = blockIdx.x * 32 + kx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (k < a.P) {
+    int c = sl;
+    for (; c + 24 < a.n; c += 32) {
+      s0 += a.part[(size_t)c * a.P + k];
+      s1 += a.part[(size_t)(c + 8) * a.P + k];
+      s2 += a.part[(size_t)(c + 16) * a.P + k];
+      s3 += a.part[(size_t)(c + 24) * a.P + k];
+    }
+    for (; c < a.n; c += 8) s0 += a.part[(size_t)c * a.P + k];
+  }
+  sh[sl][kx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (sl == 0 && k < a.P) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][kx];
+    if (a.nseg == 0) {
+      a.out[k] = s;
+    } else {
+      for (int g = 0; g < a.nseg; ++g)
+        if (k >= a.seg[g] && k < a.seg[g + 1] && a.dst[g] != nullptr) a.dst[g][k - a.seg[g]] += s;
+    }
+  }
+}
+
+static int launch_sum(const float* part, float* out, int n, int P, float* const* dst, const int* seg, int nseg, cudaStream_t st) {
+  SumArgs a{};
+  a.part = part; a.out = out; a.n = n; a.P = P; a.nseg = dst ? nseg : 0;
+  if (dst) {
+    for (int g = 0; g < nseg; ++g) a.dst[g] = dst[g];
+    for (int g = 0; g <= nseg; ++g) a.seg[g] = seg[g];
+  }
+  sum_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(a);
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
 }
 
 static int grid_for(int R, int rows_per_cta_iter) {
@@ -521,9 +560,11 @@ extern "C" int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const flo
 }
 
 extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, const float* ln_w,
-                                    const float* ln_b, const float* w_qkv, float* dx, float* dparams, int rows, int dim,
-                                    float eps, void* workspace, size_t workspace_bytes, void* stream) {
-  ERV_CHECK_ARG(x && dqkv && ln_w && ln_b && w_qkv && dx && dparams && workspace && rows > 0, "erv_block_ln_qkv_bwd: bad arguments");
+                                    const float* ln_b, const float* w_qkv, float* dx, float* dparams,
+                                    float* const* grad_accum, int rows, int dim, float eps, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  ERV_CHECK_ARG(x && dqkv && ln_w && ln_b && w_qkv && dx && (dparams || grad_accum) && workspace && rows > 0,
+                "erv_block_ln_qkv_bwd: bad arguments");
   if (dim != C) { set_error("erv_block_ln_qkv_bwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
   if (workspace_bytes < erv_block_ln_qkv_bwd_workspace(rows)) { set_error("erv_block_ln_qkv_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   LnQkvArgs a{};
@@ -535,9 +576,8 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ln_qkv_bwd_kernel<<<grid, THREADS, smem, st>>>(a);
   ERV_LAUNCH_CHECK();
-  sum_partials_kernel<<<(P_QKV + 255) / 256, 256, 0, st>>>((const float*)workspace, dparams, grid, P_QKV);
-  ERV_LAUNCH_CHECK();
-  return ERV_OK;
+  const int seg[5] = {0, QKV * C, QKV * C + QKV, QKV * C + QKV + C, P_QKV};
+  return launch_sum((const float*)workspace, dparams, grid, P_QKV, grad_accum, seg, 4, st);
 }
 
 static int fill_mlp(MlpArgs& a, const char* fn, const float* attn_out, const float* x, const float* const* params, int rows,
@@ -569,13 +609,13 @@ extern "C" int erv_block_mlp_fwd(const float* attn_out, const float* x, const fl
 }
 
 extern "C" int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, const float* const* params,
-                                 float* d_attn_out, float* dx1, float* dparams, int rows, int dim, int mlp_dim, float eps,
-                                 float p_drop, const long long* seed, int salt, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+                                 float* d_attn_out, float* dx1, float* dparams, float* const* grad_accum, int rows, int dim,
+                                 int mlp_dim, float eps, float p_drop, const long long* seed, int salt, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   MlpArgs a{};
   int rc = fill_mlp(a, "erv_block_mlp_bwd", attn_out, x, params, rows, dim, mlp_dim, eps, p_drop, seed, salt);
   if (rc) return rc;
-  ERV_CHECK_ARG(dy && d_attn_out && dx1 && dparams && workspace, "erv_block_mlp_bwd: null pointer");
+  ERV_CHECK_ARG(dy && d_attn_out && dx1 && (dparams || grad_accum) && workspace, "erv_block_mlp_bwd: null pointer");
   if (workspace_bytes < erv_block_mlp_bwd_workspace(rows)) { set_error("erv_block_mlp_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   a.dy = dy; a.da = d_attn_out; a.dx1 = dx1; a.part = (float*)workspace;
   const int grid = grid_for(rows, TILE);
@@ -584,7 +624,6 @@ extern "C" int erv_block_mlp_bwd(const float* attn_out, const float* x, const fl
   cudaStream_t st = (cudaStream_t)stream;
   mlp_bwd_kernel<<<grid, THREADS, smem, st>>>(a);
   ERV_LAUNCH_CHECK();
-  sum_partials_kernel<<<(P_MLP + 255) / 256, 256, 0, st>>>((const float*)workspace, dparams, grid, P_MLP);
-  ERV_LAUNCH_CHECK();
-  return ERV_OK;
+  const int seg[9] = {O_PROJ, O_BPROJ, O_LNW, O_LNB, O_W1, O_B1, O_W2, O_B2, P_MLP};
+  return launch_sum((const float*)workspace, dparams, grid, P_MLP, grad_accum, seg, 8, st);
 }

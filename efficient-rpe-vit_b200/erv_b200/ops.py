@@ -446,6 +446,30 @@ class _LayerNorm(torch.autograd.Function):
 
 # ---- fused block kernels (dim 32, MLP width 64): LayerNorm1 + qkv ; proj + residual + LayerNorm2 + MLP + residual ------
 FUSED_BLOCK = True  # False: the block runs op by op (Linear / LayerNorm / GELU / Dropout modules)
+# True (set by erv_b200.train.Trainer): the fused backward kernels add parameter gradients straight into the existing
+# fp32 `.grad` buffers and return None to autograd, which saves one accumulation kernel per parameter.  Only valid when
+# nothing else looks at the per-call gradients (no hooks, no create_graph); off by default.
+GRAD_INPLACE = False
+
+
+def _grad_targets(params):
+    """.grad buffers of the saved parameters when fused accumulation applies, else None."""
+    if not GRAD_INPLACE:
+        return None
+    out = []
+    for t in params:
+        if t is None:
+            out.append(None)
+            continue
+        g = t.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not t.requires_grad:
+            return None
+        out.append(g)
+    return out
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
 _drop_state = {}
 
@@ -474,23 +498,27 @@ class _BlockLnQkv(torch.autograd.Function):
         qkv = torch.empty(rows, 3 * dim, device=x.device, dtype=torch.float32)
         C.check(C.load().erv_block_ln_qkv_fwd(C.ptr(x2), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(qkv), rows, dim,
                                               float(eps), C.stream()), "block_ln_qkv")
-        ctx.save_for_backward(x2, ln_w, ln_b, w)
+        ctx.save_for_backward(x2, ln_w, ln_b, w, b)
         ctx.meta = (x.shape, float(eps), b is not None)
         return qkv.reshape(*x.shape[:-1], 3 * dim)
 
     @staticmethod
     def backward(ctx, dqkv):
-        x2, ln_w, ln_b, w = ctx.saved_tensors
+        x2, ln_w, ln_b, w, b = ctx.saved_tensors
         shape, eps, has_bias = ctx.meta
         rows, dim = x2.shape
         lib = C.load()
         dq = dqkv.reshape(rows, 3 * dim).to(torch.float32).contiguous()
         dx = torch.empty_like(x2)
-        dpar = torch.empty(lib.erv_block_ln_qkv_params(), device=x2.device, dtype=torch.float32)
         nbytes = lib.erv_block_ln_qkv_bwd_workspace(rows)
         ws = C.workspace(nbytes, x2.device)
+        tgt = _grad_targets((w, b, ln_w, ln_b))
+        dpar = None if tgt else torch.empty(lib.erv_block_ln_qkv_params(), device=x2.device, dtype=torch.float32)
         C.check(lib.erv_block_ln_qkv_bwd(C.ptr(x2), C.ptr(dq), None, C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(dx), C.ptr(dpar),
-                                         rows, dim, eps, C.ptr(ws), nbytes, C.stream()), "block_ln_qkv_bwd")
+                                         _ptr_array(tgt) if tgt else None, rows, dim, eps, C.ptr(ws), nbytes, C.stream()),
+                "block_ln_qkv_bwd")
+        if tgt:
+            return dx.reshape(shape), None, None, None, None, None
         nw = 3 * dim * dim
         dw = dpar[:nw].view(3 * dim, dim)
         db = dpar[nw:nw + 3 * dim] if has_bias else None
@@ -533,12 +561,15 @@ class _BlockMlp(torch.autograd.Function):
         lib = C.load()
         dy2 = dy.reshape(rows, dim).to(torch.float32).contiguous()
         da, dx1 = torch.empty_like(a2), torch.empty_like(x2)
-        dpar = torch.empty(lib.erv_block_mlp_params(), device=x2.device, dtype=torch.float32)
         nbytes = lib.erv_block_mlp_bwd_workspace(rows)
         ws = C.workspace(nbytes, x2.device)
+        tgt = _grad_targets(params)
+        dpar = None if tgt else torch.empty(lib.erv_block_mlp_params(), device=x2.device, dtype=torch.float32)
         C.check(lib.erv_block_mlp_bwd(C.ptr(a2), C.ptr(x2), C.ptr(dy2), _param_array(params), C.ptr(da), C.ptr(dx1), C.ptr(dpar),
-                                      rows, dim, mlp_dim, eps, p_drop, C.ptr(seed), salt, C.ptr(ws), nbytes, C.stream()),
-                "block_mlp_bwd")
+                                      _ptr_array(tgt) if tgt else None, rows, dim, mlp_dim, eps, p_drop, C.ptr(seed), salt,
+                                      C.ptr(ws), nbytes, C.stream()), "block_mlp_bwd")
+        if tgt:
+            return (da.reshape(shape), dx1.reshape(shape), *([None] * 12))
         o, grads = 0, []
         for t in params:  # dparams follows the parameter order
             grads.append(dpar[o:o + t.numel()].view(t.shape))

@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _capi as C
+from . import ops
 from .parallel import FlatParams, world_size
 
 
@@ -42,13 +43,17 @@ class Trainer:
     # ---- one optimisation step on device-resident inputs -------------------------------------------------
     def _step_impl(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.gflat.zero_()
-        if self.autocast_dtype is not None:
-            with torch.autocast("cuda", dtype=self.autocast_dtype):
+        prev, ops.GRAD_INPLACE = ops.GRAD_INPLACE, True  # fused kernels add straight into the flat gradient buffer
+        try:
+            if self.autocast_dtype is not None:
+                with torch.autocast("cuda", dtype=self.autocast_dtype):
+                    logits = self.model(images)
+            else:
                 logits = self.model(images)
-        else:
-            logits = self.model(images)
-        loss = F.cross_entropy(logits.float(), labels)
-        loss.backward()
+            loss = F.cross_entropy(logits.float(), labels)
+            loss.backward()
+        finally:
+            ops.GRAD_INPLACE = prev
         self.fp.allreduce_grad(self.group)
         self.step_count += 1
         C.check(C.load().erv_adam_step(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),

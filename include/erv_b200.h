@@ -122,12 +122,15 @@ int erv_block_supported(int dim, int mlp_dim);
 int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,
                          const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream);
 /* Backward: dx = dres (may be NULL) + d/dx ; dparams [erv_block_ln_qkv_params()] = dW_qkv [3 dim, dim] |
- * db_qkv [3 dim] | dln_w [dim] | dln_b [dim].  Recomputes the LayerNorm from x. */
+ * db_qkv [3 dim] | dln_w [dim] | dln_b [dim].  Recomputes the LayerNorm from x.  With grad_accum (4 pointers
+ * in that order, entries may be NULL) the parameter gradients are ADDED to those buffers instead and dparams
+ * may be NULL (fused accumulation into .grad). */
 int erv_block_ln_qkv_params(void);
 size_t erv_block_ln_qkv_bwd_workspace(int rows);
 int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, const float* ln_w,
-                         const float* ln_b, const float* w_qkv, float* dx, float* dparams, int rows, int dim,
-                         float eps, void* workspace, size_t workspace_bytes, void* stream);
+                         const float* ln_b, const float* w_qkv, float* dx, float* dparams,
+                         float* const* grad_accum, int rows, int dim, float eps, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* y = x1 + drop(fc2(drop(gelu(fc1(LayerNorm(x1)))))),  x1 = x + drop(attn_out w_proj^T + b_proj):
  * attention.proj + proj_dropout + residual + norm2 + mlp + residual (favor_plus.py:263-265,
  * unified_transformer.py:85-88).  params = {w_proj, b_proj, ln_w, ln_b, w_fc1, b_fc1, w_fc2, b_fc2}
@@ -138,13 +141,13 @@ int erv_block_mlp_fwd(const float* attn_out, const float* x, const float* const*
                       void* stream);
 /* Backward: recomputes the forward from (attn_out, x, seed).  d_attn_out, dx1 [rows, dim] (dx1 is the
  * gradient of the residual stream, i.e. of x); dparams [erv_block_mlp_params()] = dW_proj | db_proj |
- * dln_w | dln_b | dW_fc1 | db_fc1 | dW_fc2 | db_fc2. */
+ * dln_w | dln_b | dW_fc1 | db_fc1 | dW_fc2 | db_fc2; grad_accum (8 pointers, same order) as above. */
 int erv_block_mlp_params(void);
 size_t erv_block_mlp_bwd_workspace(int rows);
 int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, const float* const* params,
-                      float* d_attn_out, float* dx1, float* dparams, int rows, int dim, int mlp_dim, float eps,
-                      float p_drop, const long long* seed, int salt, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      float* d_attn_out, float* dx1, float* dparams, float* const* grad_accum, int rows, int dim,
+                      int mlp_dim, float eps, float p_drop, const long long* seed, int salt, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* KERPLE linear attention (favor_plus.py:197-245 + kerple.py:99-344 + fft_utils.py:112-172), evaluated
  * as Toeplitz-masked attention: A = (phi(q) phi(k)^T) * exp(bias[j-i+N-1]); out = A v / (A 1 + 1e-6)

@@ -135,3 +135,21 @@ def test_fused_block_dropout_is_consistent():
         fd = ((ops.block_mlp(*args(a0 + eps * v)) - ops.block_mlp(*args(a0 - eps * v))) * wgt).double().sum() / (2 * eps)
     an = (a0.grad * v).double().sum()
     assert abs(float(fd - an)) / abs(float(an)) < 2e-2
+
+
+def test_fused_gradient_accumulation_matches_autograd(monkeypatch):
+    """ops.GRAD_INPLACE (used by the Trainer): the backward kernels add into existing .grad buffers; two backward
+    passes must accumulate exactly like autograd's AccumulateGrad does."""
+    from erv_b200 import ops
+    blk = _make_block().eval()
+    xs = [torch.randn(4, 65, 32, device="cuda") for _ in range(2)]
+    got = []
+    for inplace in (False, True):
+        monkeypatch.setattr(ops, "GRAD_INPLACE", inplace)
+        for p in blk.parameters():
+            p.grad = torch.zeros_like(p)
+        for x in xs:
+            blk(x).square().sum().backward()
+        got.append({k: p.grad.clone() for k, p in blk.named_parameters()})
+    for k in got[0]:
+        assert rel_l2(got[1][k], got[0][k]) < 1e-6, k
