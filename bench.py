@@ -53,33 +53,69 @@ def model_cfg(w):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons of this rank's GPU every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons of this rank's GPU, polled through NVML every 5 ms while the timed region runs
+    (nvidia-smi -lms as a fallback when the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.sm_max, self.proc = index, [], set(), None, None
+        self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
-    def run(self):
+    def _poll_nvml(self):
+        n = self._nvml
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reasons.update(k for k, b in bits.items() if r & b)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.005)
+
+    def _poll_smi(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                r = [c.strip() for c in line.split(",")]
+                if r and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace(".", "").isdigit():
+                    self.sm_max = max(self.sm_max or 0.0, float(r[1]))
+                if len(r) >= 7:
+                    self.reasons.update(n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active"))
         except Exception:
             pass
 
+    def run(self):
+        if self._nvml is not None:
+            self._poll_nvml()
+        else:
+            self._poll_smi()
+
     def stop(self):
+        self._stop_evt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def cpu_reference_steps(w, batch, steps, warmup, budget_s=None):
@@ -126,7 +162,7 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="erv", choices=["erv", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
@@ -239,8 +275,14 @@ def main():
             except Exception:
                 pass
             achieved = alg_bytes / (per_call[dom] * 1e-3) / 1e9
+            traffic = None  # dram bytes per launch of this kernel at this workload, from the committed ncu capture
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    traffic = json.load(f).get(f"{args.workload}:{B}", {}).get(dom)
+            except Exception:
+                pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": src, "ms_per_launch": per_call[dom],
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": src, "ms_per_launch": per_call[dom],
                         "algorithmic_bytes": alg_bytes,
                         "attention_ms_per_step": sum(per_call.values()) * 3,
                         "per_call_ms": per_call}

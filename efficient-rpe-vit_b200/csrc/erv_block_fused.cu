@@ -59,18 +59,17 @@ __device__ __forceinline__ void gemv(const float* act, const float* Wp, int lane
     for (int t = 0; t < T; ++t) acc[m][t] = 0ull;
 #pragma unroll 2
   for (int k = 0; k < K; k += 4) {
-    u64 x01[T], x23[T];
+    u64 x01[T], x23[T];  // 64-bit views of the loaded pairs: no repacking moves
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const float4 v = ld4(act + t * AS + k);
-      x01[t] = pk(v.x, v.y);
-      x23[t] = pk(v.z, v.w);
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(act + t * AS + k);
+      x01[t] = v.x;
+      x23[t] = v.y;
     }
 #pragma unroll
     for (int m = 0; m < NOUT / 32; ++m) {
-      const float2 wa = *reinterpret_cast<const float2*>(Wp + ((k >> 1) * NOUT + lane + 32 * m) * 2);
-      const float2 wb = *reinterpret_cast<const float2*>(Wp + (((k >> 1) + 1) * NOUT + lane + 32 * m) * 2);
-      const u64 wa2 = pk(wa.x, wa.y), wb2 = pk(wb.x, wb.y);
+      const u64 wa2 = *reinterpret_cast<const u64*>(Wp + ((k >> 1) * NOUT + lane + 32 * m) * 2);
+      const u64 wb2 = *reinterpret_cast<const u64*>(Wp + (((k >> 1) + 1) * NOUT + lane + 32 * m) * 2);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         ffma2v(acc[m][t], x01[t], wa2);
@@ -107,8 +106,11 @@ __device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t st
 }
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// gelu(x) and gelu'(x) from one erf evaluation
+__device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  y = x * cdf;
+  dy = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
 struct LnQkvArgs {
@@ -385,14 +387,16 @@ __global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
     __syncwarp();
     float h[2][T];
     gemv<C, MLP, C>(sn2 + tr * C, W1, lane, h);
-    float m2[2][T];
+    float m2[2][T];  // dropout scale, then dropout scale * gelu'(h)
 #pragma unroll
     for (int t = 0; t < T; ++t)
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        h[m][t] += b1[m];
-        m2[m][t] = drop ? drop_scale(seed, s0 + 1, (uint32_t)(r0 + t) * MLP + lane + 32 * m, thresh, inv_keep) : 1.0f;
-        shd[(tr + t) * MLP + lane + 32 * m] = (r0 + t < p.R) ? gelu_f(h[m][t]) * m2[m][t] : 0.f;
+        const float ms = drop ? drop_scale(seed, s0 + 1, (uint32_t)(r0 + t) * MLP + lane + 32 * m, thresh, inv_keep) : 1.0f;
+        float gy, gd;
+        gelu_both(h[m][t] + b1[m], gy, gd);
+        shd[(tr + t) * MLP + lane + 32 * m] = (r0 + t < p.R) ? gy * ms : 0.f;
+        m2[m][t] = ms * gd;
       }
     // ---- backward through fc2
 #pragma unroll
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
     for (int t = 0; t < T; ++t)
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        const float d = dh[m][t] * m2[m][t] * gelu_grad(h[m][t]);
+        const float d = dh[m][t] * m2[m][t];
         sdh[(tr + t) * MLP + lane + 32 * m] = d;
         db1[m] += d;
       }
