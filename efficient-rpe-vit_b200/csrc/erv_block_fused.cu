@@ -134,11 +134,20 @@ __global__ void __launch_bounds__(THREADS) ln_qkv_fwd_kernel(const LnQkvArgs p) 
   for (int m = 0; m < QKV / 32; ++m) bias[m] = p.b ? __ldg(p.b + lane + 32 * m) : 0.f;
   float* a = act + warp * T * C;
   const int ntiles = (p.R + T - 1) / T;
+  float nx[T];  // rows of the next tile, in flight while this one is computed
+  {
+    const int r0 = (blockIdx.x * WARPS + warp) * T;
+#pragma unroll
+    for (int t = 0; t < T; ++t) nx[t] = (r0 + t < p.R) ? __ldg(p.x + (size_t)(r0 + t) * C + lane) : 0.f;
+  }
   for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
-    const int r0 = tile * T;
+    const int r0 = tile * T, rn = (tile + gridDim.x * WARPS) * T;
     float x[T], mean[T], rstd[T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) x[t] = (r0 + t < p.R) ? __ldg(p.x + (size_t)(r0 + t) * C + lane) : 0.f;
+    for (int t = 0; t < T; ++t) {
+      x[t] = nx[t];
+      nx[t] = (rn + t < p.R) ? __ldg(p.x + (size_t)(rn + t) * C + lane) : 0.f;
+    }
     ln_stats(x, mean, rstd, p.eps);
 #pragma unroll
     for (int t = 0; t < T; ++t) a[t * C + lane] = (x[t] - mean[t]) * rstd[t] * g + bt;
@@ -166,11 +175,9 @@ __global__ void __launch_bounds__(THREADS) ln_qkv_bwd_kernel(const LnQkvArgs p) 
   stage_bwd(Wb, p.w, QKV, C);
   __syncthreads();
   const float g = __ldg(p.ln_w + lane), bt = __ldg(p.ln_b + lane);
-  float dw[3][4];  // thread (o = tid/8 + 32 k, i0 = (tid%8)*4): dW[o][i0..i0+3]
+  u64 dw[3][2];  // thread (o = tid/8 + 32 k, i0 = (tid%8)*4): dW[o][i0..i0+3] as packed pairs (FFMA2)
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dw[k][i] = 0.f;
+  for (int k = 0; k < 3; ++k) dw[k][0] = dw[k][1] = 0ull;
   float dgam = 0.f, dbet = 0.f, dbq[QKV / 32] = {0.f, 0.f, 0.f};
   const int wo = tid >> 3, wi = (tid & 7) * 4;
   const int nct = (p.R + TILE - 1) / TILE;
@@ -214,19 +221,20 @@ __global__ void __launch_bounds__(THREADS) ln_qkv_bwd_kernel(const LnQkvArgs p) 
     // weight gradient over the CTA's 64-token tile
 #pragma unroll 4
     for (int t = 0; t < TILE; ++t) {
-      const float4 xv = ld4(sxn + t * C + wi);
+      const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(sxn + t * C + wi);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float d = sdq[t * QKV + wo + 32 * k];
-        dw[k][0] = fmaf(d, xv.x, dw[k][0]); dw[k][1] = fmaf(d, xv.y, dw[k][1]);
-        dw[k][2] = fmaf(d, xv.z, dw[k][2]); dw[k][3] = fmaf(d, xv.w, dw[k][3]);
+        const u64 dd = pk(d, d);
+        ffma2v(dw[k][0], dd, xv.x);
+        ffma2v(dw[k][1], dd, xv.y);
       }
     }
     __syncthreads();
   }
   float* part = p.part + (size_t)blockIdx.x * P_QKV;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) st4(part + (wo + 32 * k) * C + wi, make_float4(dw[k][0], dw[k][1], dw[k][2], dw[k][3]));
+  for (int k = 0; k < 3; ++k) *reinterpret_cast<ulonglong2*>(part + (wo + 32 * k) * C + wi) = make_ulonglong2(dw[k][0], dw[k][1]);
   float* rw = red + warp * (QKV + 2 * C);
 #pragma unroll
   for (int m = 0; m < QKV / 32; ++m) rw[lane + 32 * m] = dbq[m];
@@ -271,14 +279,26 @@ __global__ void __launch_bounds__(THREADS) mlp_fwd_kernel(const MlpArgs p) {
   const uint32_t s0 = (uint32_t)p.salt * 4u;
   float* aw = act + warp * T * MLP;
   const int ntiles = (p.R + T - 1) / T;
-  for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
-    const int r0 = tile * T;
-    float x[T];
+  float na[T], nx[T];  // rows of the next tile, in flight while this one is computed
+  {
+    const int r0 = (blockIdx.x * WARPS + warp) * T;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const bool ok = r0 + t < p.R;
-      aw[t * MLP + lane] = ok ? __ldg(p.a + (size_t)(r0 + t) * C + lane) : 0.f;
-      x[t] = ok ? __ldg(p.x + (size_t)(r0 + t) * C + lane) : 0.f;
+      na[t] = ok ? __ldg(p.a + (size_t)(r0 + t) * C + lane) : 0.f;
+      nx[t] = ok ? __ldg(p.x + (size_t)(r0 + t) * C + lane) : 0.f;
+    }
+  }
+  for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
+    const int r0 = tile * T, rn = (tile + gridDim.x * WARPS) * T;
+    float x[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      aw[t * MLP + lane] = na[t];
+      x[t] = nx[t];
+      const bool ok = rn + t < p.R;
+      na[t] = ok ? __ldg(p.a + (size_t)(rn + t) * C + lane) : 0.f;
+      nx[t] = ok ? __ldg(p.x + (size_t)(rn + t) * C + lane) : 0.f;
     }
     __syncwarp();
     float pr[1][T];
@@ -348,11 +368,10 @@ __global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
   const float inv_keep = drop ? 1.0f / (1.0f - p.p_drop) : 1.0f;
   const uint32_t s0 = (uint32_t)p.salt * 4u;
   // thread-owned weight-gradient entries
-  float dwp[4], dw1[8], dw2[8];
+  u64 dwp[2], dw1[4], dw2[4];  // packed pairs of consecutive input indices (FFMA2)
+  dwp[0] = dwp[1] = 0ull;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dwp[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dw1[i] = dw2[i] = 0.f;
+  for (int i = 0; i < 4; ++i) dw1[i] = dw2[i] = 0ull;
   const int po = tid >> 3, pi = (tid & 7) * 4;    // dW_proj[po][pi..+3]        (32 x 32)
   const int o1 = tid >> 2, i1 = (tid & 3) * 8;    // dW1[o1][i1..+7]            (64 x 32)
   const int o2 = tid >> 3, i2 = (tid & 7) * 8;    // dW2[o2][i2..+7]            (32 x 64)
@@ -448,30 +467,33 @@ __global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
     for (int t = 0; t < TILE; ++t) {
       {
         const float d = sdp[t * C + po];
-        const float4 v = ld4(sa + t * C + pi);
-        dwp[0] = fmaf(d, v.x, dwp[0]); dwp[1] = fmaf(d, v.y, dwp[1]); dwp[2] = fmaf(d, v.z, dwp[2]); dwp[3] = fmaf(d, v.w, dwp[3]);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sa + t * C + pi);
+        const u64 dd = pk(d, d);
+        ffma2v(dwp[0], dd, v.x); ffma2v(dwp[1], dd, v.y);
       }
       {
         const float d = sdh[t * MLP + o1];
-        const float4 v = ld4(sn2 + t * C + i1), w = ld4(sn2 + t * C + i1 + 4);
-        dw1[0] = fmaf(d, v.x, dw1[0]); dw1[1] = fmaf(d, v.y, dw1[1]); dw1[2] = fmaf(d, v.z, dw1[2]); dw1[3] = fmaf(d, v.w, dw1[3]);
-        dw1[4] = fmaf(d, w.x, dw1[4]); dw1[5] = fmaf(d, w.y, dw1[5]); dw1[6] = fmaf(d, w.z, dw1[6]); dw1[7] = fmaf(d, w.w, dw1[7]);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sn2 + t * C + i1);
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sn2 + t * C + i1 + 4);
+        const u64 dd = pk(d, d);
+        ffma2v(dw1[0], dd, v.x); ffma2v(dw1[1], dd, v.y); ffma2v(dw1[2], dd, w.x); ffma2v(dw1[3], dd, w.y);
       }
       {
         const float d = sdo[t * C + o2];
-        const float4 v = ld4(shd + t * MLP + i2), w = ld4(shd + t * MLP + i2 + 4);
-        dw2[0] = fmaf(d, v.x, dw2[0]); dw2[1] = fmaf(d, v.y, dw2[1]); dw2[2] = fmaf(d, v.z, dw2[2]); dw2[3] = fmaf(d, v.w, dw2[3]);
-        dw2[4] = fmaf(d, w.x, dw2[4]); dw2[5] = fmaf(d, w.y, dw2[5]); dw2[6] = fmaf(d, w.z, dw2[6]); dw2[7] = fmaf(d, w.w, dw2[7]);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(shd + t * MLP + i2);
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(shd + t * MLP + i2 + 4);
+        const u64 dd = pk(d, d);
+        ffma2v(dw2[0], dd, v.x); ffma2v(dw2[1], dd, v.y); ffma2v(dw2[2], dd, w.x); ffma2v(dw2[3], dd, w.y);
       }
     }
     __syncthreads();
   }
   float* part = p.part + (size_t)blockIdx.x * P_MLP;
-  st4(part + O_PROJ + po * C + pi, make_float4(dwp[0], dwp[1], dwp[2], dwp[3]));
-  st4(part + O_W1 + o1 * C + i1, make_float4(dw1[0], dw1[1], dw1[2], dw1[3]));
-  st4(part + O_W1 + o1 * C + i1 + 4, make_float4(dw1[4], dw1[5], dw1[6], dw1[7]));
-  st4(part + O_W2 + o2 * MLP + i2, make_float4(dw2[0], dw2[1], dw2[2], dw2[3]));
-  st4(part + O_W2 + o2 * MLP + i2 + 4, make_float4(dw2[4], dw2[5], dw2[6], dw2[7]));
+  *reinterpret_cast<ulonglong2*>(part + O_PROJ + po * C + pi) = make_ulonglong2(dwp[0], dwp[1]);
+  *reinterpret_cast<ulonglong2*>(part + O_W1 + o1 * C + i1) = make_ulonglong2(dw1[0], dw1[1]);
+  *reinterpret_cast<ulonglong2*>(part + O_W1 + o1 * C + i1 + 4) = make_ulonglong2(dw1[2], dw1[3]);
+  *reinterpret_cast<ulonglong2*>(part + O_W2 + o2 * MLP + i2) = make_ulonglong2(dw2[0], dw2[1]);
+  *reinterpret_cast<ulonglong2*>(part + O_W2 + o2 * MLP + i2 + 4) = make_ulonglong2(dw2[2], dw2[3]);
   float* rw = red + warp * 192;  // dbp | dgam | dbet | db1 (64) | db2
   rw[lane] = dbp; rw[32 + lane] = dgam; rw[64 + lane] = dbet; rw[96 + lane] = db1[0]; rw[128 + lane] = db1[1]; rw[160 + lane] = db2;
   __syncthreads();
