@@ -143,11 +143,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     for (int c = 0; c < NC; ++c) tmem_wait_ld8(pr[c]);
     if (favor) {
       float m_part = -INFINITY;
+      if (M < Mp) {  // padded features do not take part in the maximum
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (fbeg + c * 8 + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+          for (int i = 0; i < 8; ++i)
+            if (fbeg + c * 8 + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+      }
       ex_s[part][row] = m_part;
     }
     fence_before_sync();

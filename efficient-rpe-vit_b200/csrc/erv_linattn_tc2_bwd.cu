@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   __shared__ float ex_s[4][128];   // row-max exchange
   __shared__ float den_s[4][128];  // den partials
   __shared__ float a16_s[128];
-  __shared__ __align__(16) float o_s[128][DH];
+  __shared__ __align__(16) uint8_t o_raw[128 * DH * sizeof(T)];  // staged rows of the saved forward output (Q sweep)
   __shared__ __align__(16) float z_s[2][Mp];
   __shared__ __align__(16) float dz_s[2][Mp];
   __shared__ __align__(16) float lone_s[2][2][Mp];  // [q|k][pair side][feature]
@@ -218,24 +218,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   const uint32_t rowoff = (uint32_t)(row >> 3) * 128 + (row & 7) * 16;
   uint8_t* av_side = av + (uint32_t)side * 6 * kTokCh;  // this row's pair side: chunks 0,1 hi | 2 special | 3 zero | 4,5 lo
 
-  // ---- global rows for the next sweep -> registers, consumed after the next barrier
+  // ---- global rows for the next sweep: 16-byte cp.async copies into the (idle) x-image regions, 4 consecutive
+  // threads per 64-byte row so that a warp touches 8 rows per instruction; consumed after the next barrier.
+  // Staging: xh <- q|k rows, xl <- v|dO rows, o_raw <- saved output rows.  Lone-token rows travel in registers.
+  constexpr int RB = DH * (int)sizeof(T), CPR = RB / 16;  // row bytes, 16-byte chunks per row
   RawRow<T> nx;
   float4 nv4 = make_float4(0.f, 0.f, 0.f, 0.f);
   load_raw(qkv, nx);  // defined contents; never used before a real prefetch
   auto prefetch = [&](int g, int pass) {
     if (g >= ngroups) return;
-    const int b2 = g / H, b = 2 * b2 + side;
-    const bool ok = b < B && n < Nm;
-    if (part == 0) {
-      if (ok && !(pass == 0 && have_state)) load_raw(qkv + qkv_off(b, n, pass == 1 ? 0 : 1, h, N, H, DH), nx);
-    } else if (part == 1) {
-      if (ok && !(pass == 0 && have_state)) {
-        if (pass == 1) load_raw(dout + out_off(b, n, h, N, H, DH), nx);
-        else load_raw(qkv + qkv_off(b, n, 2, h, N, H, DH), nx);
+    const int b2 = g / H;
+    if (!(pass == 0 && have_state) && tid < 128 * CPR) {
+      const int srow = tid / CPR, sch = tid % CPR, sb = 2 * b2 + (srow >> 6), sn = srow & 63;
+      if (sb < B && sn < Nm) {
+        const int eo = sch * (16 / (int)sizeof(T));
+        const uint32_t so = (uint32_t)srow * RB + sch * 16;
+        cp_async16(xh + so, qkv + qkv_off(sb, sn, pass == 1 ? 0 : 1, h, N, H, DH) + eo);
+        if (pass == 1) {
+          cp_async16(xl + so, dout + out_off(sb, sn, h, N, H, DH) + eo);
+          cp_async16(o_raw + so, outp + out_off(sb, sn, h, N, H, DH) + eo);
+        } else {
+          cp_async16(xl + so, qkv + qkv_off(sb, sn, 2, h, N, H, DH) + eo);
+        }
       }
-    } else if (part == 2) {
-      if (ok && pass == 1) load_raw(outp + out_off(b, n, h, N, H, DH), nx);
-    } else if (lone && pass == 0) {  // warp (pair side, q|k): rows of the last token
+    }
+    cp_async_commit();
+    if (part == 3 && lone && pass == 0) {  // warp (pair side, q|k): rows of the last token
       const int lw = warp & 3, bb = 2 * b2 + (lw >> 1);
       if (bb < B) {
         load_raw(qkv + qkv_off(bb, N - 1, lw & 1, h, N, H, DH), nx);
@@ -276,12 +284,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         }
       }
       TR(pass * 100 + 0);
+      float dot = 0.f;  // part 1, Q sweep: dO . O of this row
+      if (!skip) {  // staged rows -> registers, then the staging regions become the x images again
+        cp_async_wait_all();
+        __syncthreads();
+        if (valid && part < 2) {
+          RawRow<T> r;
+          load_raw(reinterpret_cast<const T*>((part == 0 ? xh : xl) + (uint32_t)row * RB), r);
+          raw_to_f(r, rowv);
+          if (part == 1 && pass == 1) {
+            float o[DH];
+            load_raw(reinterpret_cast<const T*>(o_raw + (uint32_t)row * RB), r);
+            raw_to_f(r, o);
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dot = fmaf(rowv[d], o[d], dot);
+          }
+        }
+        __syncthreads();
+      }
       if (skip) {
         // only the lone-token rows (part 3 below) are prepared
       } else if (part == 0) {
         float n2 = INFINITY;
         if (valid) {
-          raw_to_f(nx, rowv);
           prologue_row<DH>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
           n2 = 0.f;
 #pragma unroll
@@ -291,7 +316,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         n2_s[row] = n2;
         store_x_images<DH>(xh, xl, rowv, row);
       } else if (part == 1) {
-        if (valid) raw_to_f(nx, rowv);
         if (pass != 1) {  // [v_hi | 1 | 0 | v_lo]
 #pragma unroll
           for (int c = 0; c < DH / 8; ++c) {
@@ -301,15 +325,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             store_split8(av_side, av_side + 4 * kTokCh, c * kTokCh + rowoff, ch);
           }
           *reinterpret_cast<uint4*>(av_side + 2 * kTokCh + rowoff) = make_uint4(valid ? 0x00003F80u : 0u, 0u, 0u, 0u);
-        }
-      } else if (part == 2) {
-        if (pass == 1) {
-          float o[DH];
-#pragma unroll
-          for (int d = 0; d < DH; ++d) o[d] = 0.f;
-          if (valid) raw_to_f(nx, o);
-#pragma unroll
-          for (int c = 0; c < DH / 4; ++c) st4(&o_s[row][4 * c], make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
         }
       }
       if (part == 3 && lone && pass == 0) {  // feature rows of the lone tokens: warp = (pair side, q|k), lanes over features
@@ -539,11 +554,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       for (int c = 0; c < NC; ++c) tmem_wait_ld8(pr[c]);
       if (favor) {
         float m_part = -INFINITY;
+        if (M < Mp) {  // padded features do not take part in the maximum
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (feat0(c) + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+            for (int i = 0; i < 8; ++i)
+              if (feat0(c) + i < M) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m_part = fmaxf(m_part, __uint_as_float(pr[c][i]));
+        }
         ex_s[part][row] = m_part;
       }
       fence_before_sync();
@@ -567,16 +589,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         const float n2 = n2_s[row];
         const float shift = fmaf(mx + n2, kLog2e, -log2_c);
         const float scale = (n2 < INFINITY) ? p.inv_sqrt_m : 0.f;
+        if (favor) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int f0 = feat0(c);
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float pv = __uint_as_float(pr[c][i]);
-            float v = favor ? ex2_approx(fmaf(pv, kLog2e, -shift)) : fmaxf(pv, 0.f) * scale;
-            if (f0 + i >= M) v = 0.f;
-            pr[c][i] = __float_as_uint(v);
-          }
+            for (int i = 0; i < 8; ++i)
+              pr[c][i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(pr[c][i]), kLog2e, -shift)));
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pr[c][i] = __float_as_uint(fmaxf(__uint_as_float(pr[c][i]), 0.f) * scale);
+        }
+        if (M < Mp) {  // padded features contribute nothing
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (feat0(c) + i >= M) pr[c][i] = 0u;
         }
       }
       TR(pass * 100 + 3);
@@ -713,9 +743,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         TR(104);
         if (part == 1) {
           const float r = 1.0f / ((den_s[0][row] + den_s[1][row]) + (den_s[2][row] + den_s[3][row]) + kEps);
-          float dot = 0.f;
-#pragma unroll
-          for (int d = 0; d < DH; ++d) dot = fmaf(rowv[d], o_s[row][d], dot);
 #pragma unroll
           for (int c = 0; c < DH / 8; ++c) {
             float ch[8];

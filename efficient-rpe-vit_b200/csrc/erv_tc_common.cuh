@@ -136,6 +136,13 @@ __device__ __forceinline__ float warp_sum32(float (&v)[32]) {
   return v[0];
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): no registers are held while the data is in flight
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // packed fp32 pair FMA (FFMA2 on sm_100): acc.{lo,hi} += g * w.{lo,hi}; one issue slot for two FMAs
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
