@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   __shared__ __align__(16) float lone_do[2][DH];
   __shared__ __align__(16) float lone_o[2][DH];
   __shared__ float lone_a[2][DH + 1];
+  __shared__ float lone_mx[2][2][4];  // [q|k][pair side][feature quarter]: row-max partials
+  __shared__ float lone_n2[2][2];
   __shared__ float red1_s[16];
   __shared__ float red2_s[16][DH + 1];
   __shared__ float red3_s[16][2 * DH + 1];
@@ -243,11 +245,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       }
     }
     cp_async_commit();
-    if (part == 3 && lone && pass == 0) {  // warp (pair side, q|k): rows of the last token
+    if ((part == 3 || have_state) && lone && pass == 0) {  // warp (pair side, q|k): rows of the last token
       const int lw = warp & 3, bb = 2 * b2 + (lw >> 1);
       if (bb < B) {
         load_raw(qkv + qkv_off(bb, N - 1, lw & 1, h, N, H, DH), nx);
-        if (lw & 1) {
+        if (part != 3) {
+        } else if (lw & 1) {
           if (lane < 4) nv4 = ld4(qkv + qkv_off(bb, N - 1, 2, h, N, H, DH) + 4 * lane);
         } else {
           if (lane < 4) nv4 = ld4(dout + out_off(bb, N - 1, h, N, H, DH) + 4 * lane);
@@ -327,7 +330,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           *reinterpret_cast<uint4*>(av_side + 2 * kTokCh + rowoff) = make_uint4(valid ? 0x00003F80u : 0u, 0u, 0u, 0u);
         }
       }
-      if (part == 3 && lone && pass == 0) {  // feature rows of the lone tokens: warp = (pair side, q|k), lanes over features
+      if (skip && lone) {
+        // feature rows of the lone tokens on all 16 warps: warp = (feature quarter, pair side, q|k).  Raw projections
+        // and the quarter's maximum go to shared memory; the exponentials follow after the barrier.
+        constexpr int LQ = Mp / 4;
+        const int lw = warp & 3, sp = lw >> 1, wq = lw & 1, quarter = part;
+        const bool ok = 2 * b2 + sp < B;
+        float x[DH];
+#pragma unroll
+        for (int a = 0; a < DH; ++a) x[a] = 0.f;
+        if (ok) {
+          raw_to_f(nx, x);
+          prologue_row<DH>(x, p.rot, p.ta, p.tb, h, N - 1, N, p.prescale);
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < (LQ + 31) / 32; ++i) {
+          const int fl = lane + 32 * i;
+          if (fl < LQ) {
+            const int f = quarter * LQ + fl;
+            const uint32_t wo = (uint32_t)(f >> 3) * C::X_SBO + (f & 7) * 16;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c) {
+              const float4 a = ld4(reinterpret_cast<const float*>(wh + wo + c * C::X_LBO));
+              const float4 l = ld4(reinterpret_cast<const float*>(wl + wo + c * C::X_LBO));
+              acc = fmaf(x[4 * c], a.x + l.x, acc); acc = fmaf(x[4 * c + 1], a.y + l.y, acc);
+              acc = fmaf(x[4 * c + 2], a.z + l.z, acc); acc = fmaf(x[4 * c + 3], a.w + l.w, acc);
+            }
+            lone_s[wq][sp][f] = acc;
+            if (f < M) m = fmaxf(m, acc);
+          }
+        }
+        m = warp_max(m);
+        if (lane == 0) lone_mx[wq][sp][quarter] = m;
+        if (quarter == 3) {
+          float n2 = 0.f;
+#pragma unroll
+          for (int a = 0; a < DH; ++a) n2 = fmaf(x[a], x[a], n2);
+          if (lane == 0) {
+            lone_n2[wq][sp] = 0.5f * n2;
+#pragma unroll
+            for (int c = 0; c < DH / 4; ++c) st4(&lone_x[wq][sp][4 * c], make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+          }
+          const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (wq == 1) {
+            if (lane < 4) st4(&lone_v[sp][4 * lane], ok ? nv4 : zero4);
+          } else {
+            if (lane < 4) st4(&lone_do[sp][4 * lane], ok ? nv4 : zero4);
+            else if (lane < 8) st4(&lone_o[sp][4 * (lane - 4)], ok ? nv4 : zero4);
+          }
+        }
+      } else if (part == 3 && lone && pass == 0) {  // the same on 4 warps (no saved state): warp = (pair side, q|k)
         const int lw = warp & 3, sp = lw >> 1, wq = lw & 1;  // wq: 0 = query, 1 = key
         const bool ok = 2 * b2 + sp < B;
         float x[DH];
@@ -522,6 +576,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       };
       if (skip) {  // the forward saved [S|z]: fetch this thread's feature row and go straight to the end of the sweep
         prefetch(g, 1);
+        if (lone) {  // raw projections of the lone rows -> features
+          for (int e = tid; e < 4 * Mp; e += kTcThreads) {
+            const int f = e % Mp, rw = e / Mp, wq = rw & 1, sp = rw >> 1;
+            const float mq = fmaxf(fmaxf(lone_mx[wq][sp][0], lone_mx[wq][sp][1]), fmaxf(lone_mx[wq][sp][2], lone_mx[wq][sp][3]));
+            const float pv = lone_s[wq][sp][f];
+            float v = favor ? ex2_approx(fmaf(pv, kLog2e, -fmaf(mq + lone_n2[wq][sp], kLog2e, -log2_c)))
+                            : fmaxf(pv, 0.f) * p.inv_sqrt_m;
+            if (f >= M || 2 * b2 + sp >= B) v = 0.f;
+            lone_s[wq][sp][f] = v;
+          }
+          __syncthreads();
+        }
         sweep_tail(true, st);
       } else {
       TR(pass * 100 + 1);
