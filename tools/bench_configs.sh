@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for spec in "config1 128" "config1 4096" "config3 1024" "config4 256" "config4b 256" "config5 2"; do
   set -- $spec
-  timeout 280 python bench.py --workload $1 --batch $2 --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/cfg_$1_$2.err | tail -1 > gpurun_out/cfg_$1_$2.json
+  timeout 280 python bench.py --workload $1 --batch $2 --steps 20 --warmup 3 --no-cpu-baseline 2> gpurun_out/cfg_$1_$2.err | tail -1 > gpurun_out/cfg_$1_$2.json
   python - "$1" "$2" <<'PY'
 import json,sys
 try:
