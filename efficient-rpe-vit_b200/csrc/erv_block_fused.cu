@@ -15,16 +15,10 @@
 // entries of each dW in registers and accumulates over the tile; per-CTA partials are summed by a second kernel in a
 // fixed order (deterministic, no atomics).
 // Dropout masks come from a counter hash of (seed, stream, element) so the backward regenerates them.
-#include "erv_common.cuh"
+#include "erv_block_common.cuh"
 
 namespace erv {
 namespace blk {
-
-constexpr int C = 32, QKV = 96, MLP = 64, T = 8, WARPS = 8, THREADS = 256, TILE = T * WARPS;
-constexpr int P_QKV = QKV * C + QKV + C + C;                              // dW_qkv | db_qkv | dln_w | dln_b
-constexpr int P_MLP = C * C + C + C + C + MLP * C + MLP + C * MLP + C;   // dW_proj | db_proj | dln_w | dln_b | dW1 | db1 | dW2 | db2
-constexpr int O_PROJ = 0, O_BPROJ = C * C, O_LNW = O_BPROJ + C, O_LNB = O_LNW + C, O_W1 = O_LNB + C,
-              O_B1 = O_W1 + MLP * C, O_W2 = O_B1 + MLP, O_B2 = O_W2 + C * MLP;
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -92,25 +86,6 @@ __device__ __forceinline__ void ln_stats(const float (&x)[T], float (&mean)[T], 
     const float d = x[t] - mean[t];
     rstd[t] = rsqrtf(warp_sum(d * d) * (1.0f / C) + eps);
   }
-}
-
-// counter-based dropout: keep-scale of element idx of stream `stream` (1/(1-p) or 0)
-__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t stream, uint32_t idx, uint32_t thresh, float inv_keep) {
-  uint32_t h = idx * 0x9E3779B1u + (uint32_t)seed;
-  h ^= h >> 16; h *= 0x85EBCA6Bu;
-  h += stream * 0xC2B2AE35u + (uint32_t)(seed >> 32);
-  h ^= h >> 13; h *= 0xC2B2AE35u;
-  h ^= h >> 16; h *= 0x27D4EB2Fu;
-  h ^= h >> 15;
-  return h >= thresh ? inv_keep : 0.f;
-}
-
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// gelu(x) and gelu'(x) from one erf evaluation
-__device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  y = x * cdf;
-  dy = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
 struct LnQkvArgs {
@@ -247,17 +222,6 @@ __global__ void __launch_bounds__(THREADS) ln_qkv_bwd_kernel(const LnQkvArgs p) 
     part[QKV * C + tid] = s;
   }
 }
-
-struct MlpArgs {
-  const float* a; const float* x;  // attention output (pre-projection) and block input, [R][C]
-  const float* w_proj; const float* b_proj; const float* ln_w; const float* ln_b;
-  const float* w1; const float* b1; const float* w2; const float* b2;
-  float* y;                         // fwd out
-  const float* dy;                  // bwd in
-  float* da; float* dx1; float* part;  // bwd out
-  const long long* seed; int salt;
-  int R; float eps, p_drop;
-};
 
 __global__ void __launch_bounds__(THREADS) mlp_fwd_kernel(const MlpArgs p) {
   extern __shared__ __align__(16) float sm[];
@@ -542,7 +506,7 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const SumArgs a) {
   }
 }
 
-static int launch_sum(const float* part, float* out, int n, int P, float* const* dst, const int* seg, int nseg, cudaStream_t st) {
+int launch_sum(const float* part, float* out, int n, int P, float* const* dst, const int* seg, int nseg, cudaStream_t st) {
   SumArgs a{};
   a.part = part; a.out = out; a.n = n; a.P = P; a.nseg = dst ? nseg : 0;
   if (dst) {
@@ -560,6 +524,13 @@ static int grid_for(int R, int rows_per_cta_iter) {
   return units < cap ? (units < 1 ? 1 : units) : cap;
 }
 
+}  // namespace blk
+}  // namespace erv
+
+namespace erv {
+namespace blk {
+bool mlp_bwd_tc_enabled();
+int launch_mlp_bwd_tc(const MlpArgs& a, int max_ctas, cudaStream_t st, int* grid_out);
 }  // namespace blk
 }  // namespace erv
 
@@ -644,12 +615,18 @@ extern "C" int erv_block_mlp_bwd(const float* attn_out, const float* x, const fl
   ERV_CHECK_ARG(dy && d_attn_out && dx1 && (dparams || grad_accum) && workspace, "erv_block_mlp_bwd: null pointer");
   if (workspace_bytes < erv_block_mlp_bwd_workspace(rows)) { set_error("erv_block_mlp_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   a.dy = dy; a.da = d_attn_out; a.dx1 = dx1; a.part = (float*)workspace;
+  const int seg[9] = {O_PROJ, O_BPROJ, O_LNW, O_LNB, O_W1, O_B1, O_W2, O_B2, P_MLP};
+  if (mlp_bwd_tc_enabled()) {  // tcgen05 tiles (erv_block_tc.cu)
+    int tc_grid = 0;
+    rc = launch_mlp_bwd_tc(a, grid_for(rows, TILE), (cudaStream_t)stream, &tc_grid);
+    if (rc) return rc;
+    return launch_sum((const float*)workspace, dparams, tc_grid, P_MLP, grad_accum, seg, 8, (cudaStream_t)stream);
+  }
   const int grid = grid_for(rows, TILE);
   const size_t smem = (size_t)(2 * C * C + 3 * MLP * C + 4 * TILE * C + 2 * TILE * MLP + WARPS * 192) * sizeof(float);
   ERV_CUDA(allow_smem(mlp_bwd_kernel, smem));
   cudaStream_t st = (cudaStream_t)stream;
   mlp_bwd_kernel<<<grid, THREADS, smem, st>>>(a);
   ERV_LAUNCH_CHECK();
-  const int seg[9] = {O_PROJ, O_BPROJ, O_LNW, O_LNB, O_W1, O_B1, O_W2, O_B2, P_MLP};
   return launch_sum((const float*)workspace, dparams, grid, P_MLP, grad_accum, seg, 8, st);
 }

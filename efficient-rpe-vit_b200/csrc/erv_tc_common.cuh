@@ -98,7 +98,9 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
   const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
   const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
   hi = __byte_perm(ua, ub, 0x7632);
-  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+  // the low part is rounded to nearest (magnitude half-up: + 0x8000 before the truncation) so the split error is
+  // unbiased and <= 2^-17 relative; plain truncation leaves a one-sided 2^-16
+  lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
 }
 __device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, uint32_t off, const float (&v)[8]) {
   uint4 h, l;
