@@ -530,7 +530,12 @@ static int grid_for(int R, int rows_per_cta_iter) {
 namespace erv {
 namespace blk {
 bool mlp_bwd_tc_enabled();
+void set_block_tc(int v);
 int launch_mlp_bwd_tc(const MlpArgs& a, int max_ctas, cudaStream_t st, int* grid_out);
+int launch_mlp_fwd_tc(const MlpArgs& a, cudaStream_t st);
+int launch_ln_qkv_tc(bool bwd, const float* x, const float* ln_w, const float* ln_b, const float* w, const float* b, float* qkv,
+                     const float* dqkv, const float* dres, float* dx, float* part, int rows, float eps, int max_ctas,
+                     cudaStream_t st, int* grid_out);
 }  // namespace blk
 }  // namespace erv
 
@@ -538,6 +543,7 @@ using namespace erv;
 using namespace erv::blk;
 
 extern "C" int erv_block_supported(int dim, int mlp_dim) { return dim == C && mlp_dim == MLP; }
+extern "C" void erv_block_set_tensor_core(int mode) { set_block_tc(mode); }
 extern "C" int erv_block_ln_qkv_params(void) { return P_QKV; }
 extern "C" int erv_block_mlp_params(void) { return P_MLP; }
 extern "C" size_t erv_block_ln_qkv_bwd_workspace(int rows) { return align_up((size_t)grid_for(rows, TILE) * P_QKV * sizeof(float), 256); }
@@ -547,6 +553,9 @@ extern "C" int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const flo
                                     const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream) {
   ERV_CHECK_ARG(x && ln_w && ln_b && w_qkv && qkv && rows > 0, "erv_block_ln_qkv_fwd: bad arguments");
   if (dim != C) { set_error("erv_block_ln_qkv_fwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
+  if (mlp_bwd_tc_enabled())  // tcgen05 tiles (erv_block_tc.cu)
+    return launch_ln_qkv_tc(false, x, ln_w, ln_b, w_qkv, b_qkv, qkv, nullptr, nullptr, nullptr, nullptr, rows, eps, 0,
+                            (cudaStream_t)stream, nullptr);
   LnQkvArgs a{};
   a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.w = w_qkv; a.b = b_qkv; a.qkv = qkv; a.R = rows; a.eps = eps;
   const size_t smem = (size_t)(QKV * C + WARPS * T * C) * sizeof(float);
@@ -564,6 +573,14 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
                 "erv_block_ln_qkv_bwd: bad arguments");
   if (dim != C) { set_error("erv_block_ln_qkv_bwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
   if (workspace_bytes < erv_block_ln_qkv_bwd_workspace(rows)) { set_error("erv_block_ln_qkv_bwd: workspace too small"); return ERV_E_WORKSPACE; }
+  const int seg[5] = {0, QKV * C, QKV * C + QKV, QKV * C + QKV + C, P_QKV};
+  if (mlp_bwd_tc_enabled()) {  // tcgen05 tiles (erv_block_tc.cu)
+    int tc_grid = 0;
+    int rc = launch_ln_qkv_tc(true, x, ln_w, ln_b, w_qkv, nullptr, nullptr, dqkv, dres, dx, (float*)workspace, rows, eps,
+                              grid_for(rows, TILE), (cudaStream_t)stream, &tc_grid);
+    if (rc) return rc;
+    return launch_sum((const float*)workspace, dparams, tc_grid, P_QKV, grad_accum, seg, 4, (cudaStream_t)stream);
+  }
   LnQkvArgs a{};
   a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.w = w_qkv; a.dqkv = dqkv; a.dres = dres; a.dx = dx; a.part = (float*)workspace;
   a.R = rows; a.eps = eps;
@@ -573,7 +590,6 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ln_qkv_bwd_kernel<<<grid, THREADS, smem, st>>>(a);
   ERV_LAUNCH_CHECK();
-  const int seg[5] = {0, QKV * C, QKV * C + QKV, QKV * C + QKV + C, P_QKV};
   return launch_sum((const float*)workspace, dparams, grid, P_QKV, grad_accum, seg, 4, st);
 }
 
@@ -598,6 +614,7 @@ extern "C" int erv_block_mlp_fwd(const float* attn_out, const float* x, const fl
   if (rc) return rc;
   ERV_CHECK_ARG(y, "erv_block_mlp_fwd: null output");
   a.y = y;
+  if (mlp_bwd_tc_enabled()) return launch_mlp_fwd_tc(a, (cudaStream_t)stream);  // tcgen05 tiles (erv_block_tc.cu)
   const size_t smem = (size_t)(C * C + 2 * MLP * C + WARPS * T * MLP) * sizeof(float);
   ERV_CUDA(allow_smem(mlp_fwd_kernel, smem));
   mlp_fwd_kernel<<<grid_for(rows, TILE), THREADS, smem, (cudaStream_t)stream>>>(a);

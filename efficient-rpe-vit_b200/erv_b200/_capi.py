@@ -40,6 +40,7 @@ SIGNATURES = {
     "erv_linear_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _Z, _P]),
     "erv_linear_attention_state_floats": (c_size_t, [_I, _I, _I, _I, _I]),
     "erv_block_supported": (c_int, [_I, _I]),
+    "erv_block_set_tensor_core": (None, [_I]),
     "erv_block_ln_qkv_params": (c_int, []),
     "erv_block_mlp_params": (c_int, []),
     "erv_block_ln_qkv_bwd_workspace": (c_size_t, [_I]),

@@ -117,6 +117,9 @@ int erv_linear_attention_bwd(const void* qkv, const void* out, const void* dout,
 
 /* 1 when the fused block kernels below cover these dims (the reference's: configs/datasets/mnist.py:20-24). */
 int erv_block_supported(int dim, int mlp_dim);
+/* Kernel family behind the four block calls: 1 = tcgen05 tiles (default), 0 = fp32 FFMA2 register tiles,
+ * -1 = default / ERV_DISABLE_BLOCK_TC environment variable.  Both compute the same functions. */
+void erv_block_set_tensor_core(int mode);
 /* qkv [rows, 3*dim] = LayerNorm(x; ln_w, ln_b, eps) w_qkv^T (+ b_qkv, may be NULL): norm1 + attention.qkv
  * (unified_transformer.py:75-83, favor_plus.py:174).  fp32, x [rows, dim]. */
 int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,

@@ -117,7 +117,7 @@ def test_fused_block_dropout_is_consistent():
     y = ops.block_mlp(a, x, eye, zero, ones, zero, w1, b1, w2, zero, 1e-5, 0.25, seed)
     kept = (y != 0).float().mean().item()
     assert abs(kept - 0.75) < 0.01
-    assert torch.allclose(y[y != 0], (a / 0.75)[y != 0], rtol=1e-5)
+    assert torch.allclose(y[y != 0], (a / 0.75)[y != 0], rtol=1e-4, atol=1e-6)  # split-bf16 tensor-core product
     y2 = ops.block_mlp(a, x, eye, zero, ones, zero, w1, b1, w2, zero, 1e-5, 0.25, seed + 1)
     assert ((y != 0) != (y2 != 0)).float().mean().item() > 0.2
     # full block: gradient along a random direction equals the central difference with the masks held fixed
