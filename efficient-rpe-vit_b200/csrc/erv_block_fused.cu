@@ -15,6 +15,8 @@
 // entries of each dW in registers and accumulates over the tile; per-CTA partials are summed by a second kernel in a
 // fixed order (deterministic, no atomics).
 // Dropout masks come from a counter hash of (seed, stream, element) so the backward regenerates them.
+#include <initializer_list>
+
 #include "erv_block_common.cuh"
 
 namespace erv {
@@ -549,9 +551,16 @@ extern "C" int erv_block_mlp_params(void) { return P_MLP; }
 extern "C" size_t erv_block_ln_qkv_bwd_workspace(int rows) { return align_up((size_t)grid_for(rows, TILE) * P_QKV * sizeof(float), 256); }
 extern "C" size_t erv_block_mlp_bwd_workspace(int rows) { return align_up((size_t)grid_for(rows, TILE) * P_MLP * sizeof(float), 256); }
 
+static bool aligned16(std::initializer_list<const void*> ptrs) {
+  for (const void* q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+  return true;
+}
+
 extern "C" int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,
                                     const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream) {
   ERV_CHECK_ARG(x && ln_w && ln_b && w_qkv && qkv && rows > 0, "erv_block_ln_qkv_fwd: bad arguments");
+  ERV_CHECK_ARG(aligned16({x, ln_w, ln_b, w_qkv, b_qkv, qkv}), "erv_block_ln_qkv_fwd: pointers must be 16-byte aligned");
   if (dim != C) { set_error("erv_block_ln_qkv_fwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
   if (mlp_bwd_tc_enabled())  // tcgen05 tiles (erv_block_tc.cu)
     return launch_ln_qkv_tc(false, x, ln_w, ln_b, w_qkv, b_qkv, qkv, nullptr, nullptr, nullptr, nullptr, rows, eps, 0,
@@ -571,6 +580,7 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
                                     size_t workspace_bytes, void* stream) {
   ERV_CHECK_ARG(x && dqkv && ln_w && ln_b && w_qkv && dx && (dparams || grad_accum) && workspace && rows > 0,
                 "erv_block_ln_qkv_bwd: bad arguments");
+  ERV_CHECK_ARG(aligned16({x, dqkv, dres, ln_w, ln_b, w_qkv, dx, workspace}), "erv_block_ln_qkv_bwd: pointers must be 16-byte aligned");
   if (dim != C) { set_error("erv_block_ln_qkv_bwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
   if (workspace_bytes < erv_block_ln_qkv_bwd_workspace(rows)) { set_error("erv_block_ln_qkv_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   const int seg[5] = {0, QKV * C, QKV * C + QKV, QKV * C + QKV + C, P_QKV};
@@ -597,6 +607,8 @@ static int fill_mlp(MlpArgs& a, const char* fn, const float* attn_out, const flo
                     int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt) {
   ERV_CHECK_ARG(attn_out && x && params && rows > 0, "%s: bad arguments", fn);
   for (int i = 0; i < 8; ++i) ERV_CHECK_ARG(params[i], "%s: parameter %d is null", fn, i);
+  for (int i = 0; i < 8; ++i) ERV_CHECK_ARG(aligned16({params[i]}), "%s: parameter %d must be 16-byte aligned", fn, i);
+  ERV_CHECK_ARG(aligned16({attn_out, x}), "%s: pointers must be 16-byte aligned", fn);
   ERV_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed), "%s: dropout %g needs 0 <= p < 1 and a seed", fn, (double)p_drop);
   if (dim != C || mlp_dim != MLP) { set_error("%s: dims (%d, %d) not supported (32, 64)", fn, dim, mlp_dim); return ERV_E_UNSUPPORTED; }
   a.a = attn_out; a.x = x;
@@ -612,7 +624,7 @@ extern "C" int erv_block_mlp_fwd(const float* attn_out, const float* x, const fl
   MlpArgs a{};
   int rc = fill_mlp(a, "erv_block_mlp_fwd", attn_out, x, params, rows, dim, mlp_dim, eps, p_drop, seed, salt);
   if (rc) return rc;
-  ERV_CHECK_ARG(y, "erv_block_mlp_fwd: null output");
+  ERV_CHECK_ARG(y && aligned16({y}), "erv_block_mlp_fwd: null or misaligned output");
   a.y = y;
   if (mlp_bwd_tc_enabled()) return launch_mlp_fwd_tc(a, (cudaStream_t)stream);  // tcgen05 tiles (erv_block_tc.cu)
   const size_t smem = (size_t)(C * C + 2 * MLP * C + WARPS * T * MLP) * sizeof(float);
@@ -630,6 +642,7 @@ extern "C" int erv_block_mlp_bwd(const float* attn_out, const float* x, const fl
   int rc = fill_mlp(a, "erv_block_mlp_bwd", attn_out, x, params, rows, dim, mlp_dim, eps, p_drop, seed, salt);
   if (rc) return rc;
   ERV_CHECK_ARG(dy && d_attn_out && dx1 && (dparams || grad_accum) && workspace, "erv_block_mlp_bwd: null pointer");
+  ERV_CHECK_ARG(aligned16({dy, d_attn_out, dx1, workspace}), "erv_block_mlp_bwd: pointers must be 16-byte aligned");
   if (workspace_bytes < erv_block_mlp_bwd_workspace(rows)) { set_error("erv_block_mlp_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   a.dy = dy; a.da = d_attn_out; a.dx1 = dx1; a.part = (float*)workspace;
   const int seg[9] = {O_PROJ, O_BPROJ, O_LNW, O_LNB, O_W1, O_B1, O_W2, O_B2, P_MLP};

@@ -21,7 +21,11 @@ def shard_slice(global_batch: int, rank: int, world: int) -> slice:
 
 
 class FlatParams:
-    """Re-homes the trainable parameters of a module (and their .grad) as views of two flat fp32 buffers."""
+    """Re-homes the trainable parameters of a module (and their .grad) as views of two flat fp32 buffers.  Every
+    parameter starts on a 16-byte boundary (the kernels read parameter vectors with 128-bit loads; KERPLE's
+    rel_pos_bias has 2(2N-1) elements and would misalign everything behind it); the padding stays zero."""
+
+    ALIGN = 4  # floats
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -29,15 +33,16 @@ class FlatParams:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.sizes = [p.numel() for p in self.params]
-        total = sum(self.sizes)
-        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.offsets, total = [], 0
+        for n in self.sizes:
+            self.offsets.append(total)
+            total += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
-        off = 0
-        for p, n in zip(self.params, self.sizes):
+        for p, n, off in zip(self.params, self.sizes, self.offsets):
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)
             p.grad = self.grad[off:off + n].view_as(p)
-            off += n
 
     def numel(self) -> int:
         return self.flat.numel()

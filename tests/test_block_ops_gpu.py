@@ -153,3 +153,18 @@ def test_fused_gradient_accumulation_matches_autograd(monkeypatch):
         got.append({k: p.grad.clone() for k, p in blk.named_parameters()})
     for k in got[0]:
         assert rel_l2(got[1][k], got[0][k]) < 1e-6, k
+
+
+def test_trainer_with_flat_parameters_and_kerple():
+    """KERPLE's rel_pos_bias has 2(2N-1) elements: the flat parameter buffer must keep every parameter 16-byte aligned
+    for the fused block kernels (regression: misaligned address at BASELINE configs 3 and 5)."""
+    from erv_b200 import MNIST_CONFIG, create_model
+    from erv_b200.train import Trainer
+    torch.manual_seed(0)
+    model = create_model("performer_relu_most_general", MNIST_CONFIG).to("cuda").train()
+    tr = Trainer(model, lr=1e-3, use_graph=False)
+    for p in tr.params:
+        assert p.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0
+    img, lab = torch.randn(16, 1, 28, 28, device="cuda"), torch.randint(0, 10, (16,), device="cuda")
+    losses = [float(tr.step(img, lab)) for _ in range(5)]
+    assert all(l == l and l < 100 for l in losses) and losses[-1] < losses[0]

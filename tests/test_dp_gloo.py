@@ -63,7 +63,9 @@ def test_flat_allreduce_matches_single_process():
 def test_flat_params_are_views_and_shards_validate():
     m = _model(1)
     fp = FlatParams(m.parameters())
-    assert fp.numel() == sum(p.numel() for p in m.parameters())
+    n_par = sum(p.numel() for p in m.parameters())
+    assert n_par <= fp.numel() < n_par + 4 * len(fp.params)  # every parameter starts on a 16-byte boundary
+    assert all(o % 4 == 0 for o in fp.offsets) and all(p.data_ptr() % 16 == 0 for p in fp.params)
     m[0].weight.data.fill_(2.0)
     assert (fp.flat[:30] == 2.0).all()           # parameter storage is the flat buffer
     m(torch.randn(4, 6)).sum().backward()

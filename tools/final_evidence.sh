@@ -5,7 +5,7 @@ TAG=${1:-r01_final}
 mkdir -p gpurun_out
 python bench.py --steps 100 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { tail -5 gpurun_out/bench_$TAG.err; exit 1; }
 tail -1 gpurun_out/bench_$TAG.json | cut -c1-400
-for spec in "la_tc2_fwd_kernel fwd" "la_tc2_bwd_kernel bwd" "mlp_bwd_kernel mlpbwd"; do
+for spec in "la_tc2_fwd_kernel fwd" "la_tc2_bwd_kernel bwd" "mlp_bwd_tc_kernel mlpbwd"; do
   set -- $spec
   ncu --set full --clock-control none --import-source on -k regex:$1 -s 4 -c 1 -f -o gpurun_out/prof_${TAG}_$2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${TAG}_$2.log 2>&1
 done
