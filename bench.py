@@ -238,13 +238,19 @@ def main():
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- e2e: host buffers in, loss out, every step ------------------------------------------------------
+    # Every step's batch starts in pinned host memory and its loss is read back on the host; the copy of batch i+1 is
+    # issued (side stream, double-buffered staging) before the host waits for the loss of batch i, as a data loader
+    # with pin_memory / non_blocking copies does.
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     for i in range(2):
         trainer.step(*host_pool[i % len(host_pool)])
     barrier()
     t0 = time.perf_counter()
+    trainer.prefetch(*host_pool[0])
     for i in range(args.steps):
-        l = trainer.step(*host_pool[i % len(host_pool)])
+        l = trainer.step_prefetched()
+        if i + 1 < args.steps:
+            trainer.prefetch(*host_pool[(i + 1) % len(host_pool)])
         loss_host.copy_(l, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
     barrier()

@@ -92,6 +92,49 @@ class Trainer:
         self._graph.replay()
         return self._loss
 
+    # ---- host-fed training: the next batch's host->device copy overlaps the current step ----------------------------
+    def prefetch(self, images: torch.Tensor, labels: torch.Tensor):
+        """Start the asynchronous copy of a (pinned) host batch into one of two device staging buffers on a side stream.
+        The matching step_prefetched() call consumes it.  This is the data-loader pattern of the reference's training
+        loop (pin_memory + non_blocking copies, experiments/utils/training.py:53-57) with the copy taken off the compute
+        stream."""
+        dev = self.flat.device
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [(torch.empty(images.shape, dtype=images.dtype, device=dev),
+                            torch.empty(labels.shape, dtype=labels.dtype, device=dev)) for _ in range(2)]
+            self._stage_events = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_put, self._stage_get = 0, 0
+        slot = self._stage_put % 2
+        if self._stage_put >= 2:  # the step that read this slot two prefetches ago must have consumed it
+            self._copy_stream.wait_event(self._stage_free[slot])
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[slot][0].copy_(images, non_blocking=True)
+            self._stage[slot][1].copy_(labels, non_blocking=True)
+            self._stage_events[slot].record(self._copy_stream)
+        self._stage_put += 1
+
+    def step_prefetched(self) -> torch.Tensor:
+        """One optimisation step on the oldest prefetched batch."""
+        assert hasattr(self, "_stage") and self._stage_get < self._stage_put, "call prefetch() first"
+        slot = self._stage_get % 2
+        self._stage_get += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_events[slot])
+        img, lab = self._stage[slot]
+        if not self.use_graph:
+            loss = self._step_impl(img, lab)
+        else:
+            if self._graph is None:
+                self._capture(img, lab)
+            self._static[0].copy_(img, non_blocking=True)  # device-to-device, a few microseconds
+            self._static[1].copy_(lab, non_blocking=True)
+            self._graph.replay()
+            loss = self._loss
+        self._stage_free[slot].record(cur)
+        return loss
+
     def kernels_per_step(self) -> Optional[int]:
         """erv kernels launched per step in graph mode (counted while the graph was recorded)."""
         return getattr(self, "graph_kernels", None)

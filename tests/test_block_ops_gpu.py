@@ -168,3 +168,27 @@ def test_trainer_with_flat_parameters_and_kerple():
     img, lab = torch.randn(16, 1, 28, 28, device="cuda"), torch.randint(0, 10, (16,), device="cuda")
     losses = [float(tr.step(img, lab)) for _ in range(5)]
     assert all(l == l and l < 100 for l in losses) and losses[-1] < losses[0]
+
+
+def test_prefetched_steps_equal_direct_steps():
+    """Trainer.prefetch / step_prefetched (host batches copied on a side stream) train exactly like Trainer.step."""
+    from erv_b200 import MNIST_CONFIG, create_model
+    from erv_b200.train import Trainer
+    batches = [(torch.randn(8, 1, 28, 28).pin_memory(), torch.randint(0, 10, (8,)).pin_memory()) for _ in range(4)]
+    losses = []
+    for mode in ("direct", "prefetched"):
+        torch.manual_seed(0)
+        tr = Trainer(create_model("performer_favor", MNIST_CONFIG, dropout=0.0).to("cuda").train(), use_graph=True)
+        out = []
+        if mode == "direct":
+            for b in batches:
+                out.append(float(tr.step(*b)))
+        else:
+            tr.prefetch(*batches[0])
+            for i in range(len(batches)):
+                l = tr.step_prefetched()
+                if i + 1 < len(batches):
+                    tr.prefetch(*batches[i + 1])
+                out.append(float(l))
+        losses.append(out)
+    assert losses[0] == losses[1]
