@@ -39,6 +39,13 @@ SIGNATURES = {
     "erv_linear_attention_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _Z, _P]),
     "erv_linear_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _Z, _P]),
     "erv_linear_attention_state_floats": (c_size_t, [_I, _I, _I, _I, _I]),
+    "erv_embed_supported": (c_int, [_I, _I]),
+    "erv_embed_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "erv_embed_bwd_workspace": (c_size_t, [_I, _I, _I, _I]),
+    "erv_embed_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "erv_head_loss_workspace": (c_size_t, [_I, _I]),
+    "erv_head_loss_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _Z, _P]),
+    "erv_head_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _Z, _P]),
     "erv_block_supported": (c_int, [_I, _I]),
     "erv_block_set_tensor_core": (None, [_I]),
     "erv_block_ln_qkv_params": (c_int, []),

@@ -446,6 +446,9 @@ class _LayerNorm(torch.autograd.Function):
 
 # ---- fused block kernels (dim 32, MLP width 64): LayerNorm1 + qkv ; proj + residual + LayerNorm2 + MLP + residual ------
 FUSED_BLOCK = True  # False: the block runs op by op (Linear / LayerNorm / GELU / Dropout modules)
+# The fused patch-embedding kernels (csrc/erv_embed_head.cu) are correct but, as plain FMA kernels with per-token gathers,
+# not yet faster than the library chain they replace (168 us for the weight gradient at config 2): off by default.
+FUSED_EMBED = False
 # True (set by erv_b200.train.Trainer): the fused backward kernels add parameter gradients straight into the existing
 # fp32 `.grad` buffers and return None to autograd, which saves one accumulation kernel per parameter.  Only valid when
 # nothing else looks at the per-call gradients (no hooks, no create_graph); off by default.
@@ -579,6 +582,89 @@ class _BlockMlp(torch.autograd.Function):
 
 def block_mlp(a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, p_drop=0.0, seed=None, salt=0):
     return _BlockMlp.apply(a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps, p_drop, seed, salt)
+
+
+# ---- the two ends of the ViT: patch embedding + CLS + positions ; final LayerNorm + classifier + cross-entropy -------------
+class _Embed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, w, b, cls, pos, patch):
+        C.require_cuda(images, w)
+        images = images.contiguous()
+        bsz, cin, s, _ = images.shape
+        n = (s // patch) ** 2 + 1
+        out = torch.empty(bsz, n, w.shape[0], device=images.device, dtype=torch.float32)
+        C.check(C.load().erv_embed_fwd(C.ptr(images), C.ptr(w), C.ptr(b), C.ptr(cls), C.ptr(pos), C.ptr(out), bsz, cin, s, patch,
+                                       C.stream()), "embed")
+        ctx.save_for_backward(images, w, b, cls, pos)
+        ctx.patch = patch
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        images, w, b, cls, pos = ctx.saved_tensors
+        bsz, cin, s, _ = images.shape
+        lib = C.load()
+        dout = dout.to(torch.float32).contiguous()
+        tgt = _grad_targets((w, b, cls, pos))
+        grads = tgt if tgt else [torch.empty_like(t) for t in (w, b, cls, pos)]
+        nbytes = lib.erv_embed_bwd_workspace(bsz, cin, s, ctx.patch)
+        ws = C.workspace(nbytes, images.device)
+        C.check(lib.erv_embed_bwd(C.ptr(images), C.ptr(dout), *[C.ptr(g) for g in grads], 1 if tgt else 0, bsz, cin, s, ctx.patch,
+                                  C.ptr(ws), nbytes, C.stream()), "embed_bwd")
+        if tgt:
+            return None, None, None, None, None, None
+        return (None, *grads, None)
+
+
+def embed(images, w, b, cls, pos, patch):
+    return _Embed.apply(images, w, b, cls, pos, patch)
+
+
+def embed_supported(dim: int, patch_dim: int) -> bool:
+    return bool(C.load().erv_embed_supported(int(dim), int(patch_dim)))
+
+
+class _HeadLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b, labels, eps):
+        C.require_cuda(x, w, labels)
+        x = x.contiguous()
+        bsz, n, dim = x.shape
+        labels = labels.to(torch.int64).contiguous()
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        lib = C.load()
+        nbytes = lib.erv_head_loss_workspace(bsz, w.shape[0])
+        ws = C.workspace(nbytes, x.device)
+        C.check(lib.erv_head_loss_fwd(C.ptr(x), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(labels), C.ptr(loss), bsz, n,
+                                      dim, w.shape[0], float(eps), C.ptr(ws), nbytes, C.stream()), "head_loss")
+        ctx.save_for_backward(x, ln_w, ln_b, w, b, labels)
+        ctx.eps = float(eps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, ln_w, ln_b, w, b, labels = ctx.saved_tensors
+        bsz, n, dim = x.shape
+        k = w.shape[0]
+        dloss = dloss.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        tgt = _grad_targets((w, b, ln_w, ln_b))
+        dpar = None if tgt else torch.empty(k * dim + k + 2 * dim, device=x.device, dtype=torch.float32)
+        lib = C.load()
+        nbytes = lib.erv_head_loss_workspace(bsz, k)
+        ws = C.workspace(nbytes, x.device)
+        C.check(lib.erv_head_loss_bwd(C.ptr(x), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(labels), C.ptr(dloss),
+                                      C.ptr(dx), C.ptr(dpar), _ptr_array(tgt) if tgt else None, bsz, n, dim, k, ctx.eps,
+                                      C.ptr(ws), nbytes, C.stream()), "head_loss_bwd")
+        if tgt:
+            return dx, None, None, None, None, None, None
+        o = k * dim
+        return dx, dpar[o + k:o + k + dim], dpar[o + k + dim:], dpar[:o].view(k, dim), dpar[o:o + k], None, None
+
+
+def head_loss(x, ln_w, ln_b, w, b, labels, eps=1e-5):
+    """mean cross-entropy of Linear(LayerNorm(x[:, 0])) against labels, as one kernel (and one for the backward)."""
+    return _HeadLoss.apply(x, ln_w, ln_b, w, b, labels, eps)
 
 
 def layer_norm(x, weight, bias, eps=1e-5):

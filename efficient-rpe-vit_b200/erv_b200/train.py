@@ -48,9 +48,11 @@ class Trainer:
             if self.autocast_dtype is not None:
                 with torch.autocast("cuda", dtype=self.autocast_dtype):
                     logits = self.model(images)
+                loss = F.cross_entropy(logits.float(), labels)
+            elif hasattr(self.model, "loss"):
+                loss = self.model.loss(images, labels)  # head + criterion fused when the model supports it
             else:
-                logits = self.model(images)
-            loss = F.cross_entropy(logits.float(), labels)
+                loss = F.cross_entropy(self.model(images).float(), labels)
             loss.backward()
         finally:
             ops.GRAD_INPLACE = prev

@@ -109,12 +109,39 @@ class BaseViT(nn.Module):
         x = x.reshape(b, c, h // p, p, w // p, p).permute(0, 2, 4, 1, 3, 5)
         return x.reshape(b, self.num_patches, self.patch_dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.patch_embedding(self.patchify(x))
-        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding
+    def _fused_ends(self, x: torch.Tensor) -> bool:
+        """The embedding / head+loss kernels of csrc/erv_embed_head.cu apply (fp32 CUDA, dim 32, no autocast)."""
+        return (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled()
+                and self.patch_embedding.weight.dtype == torch.float32 and self.patch_embedding.bias is not None
+                and ops.embed_supported(self.dim, self.patch_dim))
+
+    def features(self, x: torch.Tensor) -> torch.Tensor:
+        """images -> token features after the last block [B, N, dim]."""
+        if ops.FUSED_EMBED and self._fused_ends(x):
+            b, c, h, w = x.shape
+            assert c == self.in_channels, f"Expected {self.in_channels} channels, got {c}"
+            assert h == self.image_size and w == self.image_size, \
+                f"Expected {self.image_size}x{self.image_size} images, got {h}x{w}"
+            x = ops.embed(x, self.patch_embedding.weight, self.patch_embedding.bias, self.cls_token.reshape(-1),
+                          self.pos_embedding.reshape(-1, self.dim), self.patch_size)
+        else:
+            x = self.patch_embedding(self.patchify(x))
+            x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding
         for block in self.transformer_blocks:
             x = block(x)
-        return self.mlp_head(x[:, 0])
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.mlp_head(self.features(x)[:, 0])
+
+    def loss(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """Mean cross-entropy of forward(images) against labels (the reference's training criterion,
+        experiments/utils/training.py:57-60), with the final LayerNorm, classifier and loss in one kernel when possible."""
+        x = self.features(images)
+        ln, fc = self.mlp_head[0], self.mlp_head[1]
+        if self._fused_ends(images) and fc.bias is not None and fc.out_features <= 32:
+            return ops.head_loss(x, ln.weight, ln.bias, fc.weight, fc.bias, labels, ln.eps)
+        return torch.nn.functional.cross_entropy(self.mlp_head(x[:, 0]).float(), labels)
 
     def count_parameters(self) -> Dict[str, int]:
         total = sum(p.numel() for p in self.parameters())

@@ -152,6 +152,32 @@ int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, co
                       int mlp_dim, float eps, float p_drop, const long long* seed, int salt, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- the two ends of the ViT, model dim 32 ------------------------------------ */
+
+/* x [B, N, 32] = patch embedding + CLS + position embedding (base_vit.py:190-223): x[b,0] = cls + pos[0];
+ * x[b,1+p] = patch(b,p) w^T + bias + pos[1+p], patches in raster order, patch element k = c P^2 + i P + j.
+ * images [B, Cin, S, S] fp32, w [32, Cin P^2], N = (S/P)^2 + 1. */
+int erv_embed_supported(int dim, int patch_dim);
+int erv_embed_fwd(const float* images, const float* w, const float* b, const float* cls, const float* pos,
+                  float* out, int B, int Cin, int S, int P, void* stream);
+size_t erv_embed_bwd_workspace(int B, int Cin, int S, int P);
+/* Gradients of the four parameters from dout [B, N, 32]; accumulate != 0 adds to the buffers' contents. */
+int erv_embed_bwd(const float* images, const float* dout, float* dw, float* db, float* dcls, float* dpos,
+                  int accumulate, int B, int Cin, int S, int P, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* loss = mean_b CrossEntropy(Linear(LayerNorm(x[b, 0])), labels[b]) (base_vit.py:230-233 + the training loop's
+ * criterion, training.py:57-60).  x [B, N, dim], w [K, dim], labels int64 [B], loss: one float on the device. */
+size_t erv_head_loss_workspace(int B, int K);
+int erv_head_loss_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w, const float* b,
+                      const long long* labels, float* loss, int B, int N, int dim, int K, float eps, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Backward: dx [B, N, dim] is fully written (zero except token 0); dparams = dW [K, dim] | db [K] | dln_w | dln_b,
+ * or added to the 4 grad_accum buffers.  dloss: one float on the device. */
+int erv_head_loss_bwd(const float* x, const float* ln_w, const float* ln_b, const float* w, const float* b,
+                      const long long* labels, const float* dloss, float* dx, float* dparams,
+                      float* const* grad_accum, int B, int N, int dim, int K, float eps, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* KERPLE linear attention (favor_plus.py:197-245 + kerple.py:99-344 + fft_utils.py:112-172), evaluated
  * as Toeplitz-masked attention: A = (phi(q) phi(k)^T) * exp(bias[j-i+N-1]); out = A v / (A 1 + 1e-6)
  * with q, k L2-normalised.  rel_pos_bias [H, 2N-1].  den_out [B, H, N] is saved for the backward. */

@@ -192,3 +192,34 @@ def test_prefetched_steps_equal_direct_steps():
                 out.append(float(l))
         losses.append(out)
     assert losses[0] == losses[1]
+
+
+# ---- the two ends of the ViT (csrc/erv_embed_head.cu) --------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,patch,bsz", [("mnist", 7, 5), ("cifar", 4, 6), ("cifar", 8, 3)])
+def test_fused_embed_and_head_loss_match_library_path(cfg, patch, bsz, monkeypatch):
+    """model.loss(images, labels) with the fused embedding / head+loss kernels against the same model run op by op:
+    loss and every parameter gradient (MNIST patch dim 49 is not a multiple of 8; CIFAR patch 8 is the 192-wide case)."""
+    from erv_b200 import CIFAR10_CONFIG, MNIST_CONFIG, create_model, ops
+    torch.manual_seed(4)
+    base = MNIST_CONFIG if cfg == "mnist" else CIFAR10_CONFIG
+    model = create_model("performer_favor", base, patch_size=patch, dropout=0.0).to("cuda").eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.normal_(0.3, 0.3)
+    s, c = (28, 1) if cfg == "mnist" else (32, 3)
+    img, lab = torch.randn(bsz, c, s, s, device="cuda"), torch.randint(0, 10, (bsz,), device="cuda")
+    res = []
+    for fused in (True, False):
+        monkeypatch.setattr(ops, "FUSED_BLOCK", fused)
+        monkeypatch.setattr(ops, "FUSED_EMBED", fused)
+        model.zero_grad()
+        loss = model.loss(img, lab)
+        loss.backward()
+        res.append((loss.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}))
+    assert abs(float(res[0][0]) - float(res[1][0])) < 1e-5
+    for k in res[1][1]:
+        assert rel_l2(res[0][1][k], res[1][1][k]) < 5e-5, k
+    monkeypatch.setattr(ops, "FUSED_BLOCK", True)
+    logits = model(img)  # the plain forward keeps its meaning
+    assert abs(float(torch.nn.functional.cross_entropy(logits, lab)) - float(res[0][0])) < 1e-5
