@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   __shared__ float ex_s[4][128];   // row-max exchange
   __shared__ float den_s[4][128];  // den partials
   __shared__ float a16_s[128];
-  __shared__ __align__(16) uint8_t o_raw[128 * DH * sizeof(T)];  // staged rows of the saved forward output (Q sweep)
+  // staged rows of the saved forward output (Q sweep); after the dot products the same rows hold dO in fp32
+  __shared__ __align__(16) uint8_t o_raw[128 * DH * sizeof(float)];
+  __shared__ __align__(16) float xrow_s[128][DH];  // prepared q / k rows (kept out of registers across the sweep)
   __shared__ __align__(16) float z_s[2][Mp];
   __shared__ __align__(16) float dz_s[2][Mp];
   __shared__ __align__(16) float lone_s[2][2][Mp];  // [q|k][pair side][feature]
@@ -270,10 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 
     for (int pass = 0; pass < 3; ++pass) {  // 0: K1 (build S), 1: Q (dS, dq), 2: K2 (dv, dk)
       const int which = (pass == 1) ? 0 : 1;
-      // ---- step 1: consume the prefetched rows.  part 0 keeps the prepared q/k row, part 1 the dO row (Q sweep)
-      float rowv[DH];
-#pragma unroll
-      for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
+      // ---- step 1: consume the prefetched rows (prepared q/k rows -> xrow_s, dO rows of the Q sweep -> o_raw)
       const bool skip = pass == 0 && have_state;  // S comes from the forward: no K1 sweep
       float st[DH + 1];  // skip: this thread's feature row of the saved [S|z], in flight across the first barrier
 #pragma unroll
@@ -289,6 +288,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       TR(pass * 100 + 0);
       float dot = 0.f;  // part 1, Q sweep: dO . O of this row
       if (!skip) {  // staged rows -> registers, then the staging regions become the x images again
+        float rowv[DH];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) rowv[d] = 0.f;
         cp_async_wait_all();
         __syncthreads();
         if (valid && part < 2) {
@@ -303,11 +305,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             for (int d = 0; d < DH; ++d) dot = fmaf(rowv[d], o[d], dot);
           }
         }
+        if (part == 1 && pass == 1) {  // own row only: no other thread reads it
+          float* od = reinterpret_cast<float*>(o_raw) + row * DH;
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) st4(od + 4 * c, make_float4(rowv[4 * c], rowv[4 * c + 1], rowv[4 * c + 2], rowv[4 * c + 3]));
+        }
         __syncthreads();
-      }
-      if (skip) {
-        // only the lone-token rows (part 3 below) are prepared
-      } else if (part == 0) {
+      if (part == 0) {
         float n2 = INFINITY;
         if (valid) {
           prologue_row<DH>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
@@ -318,6 +322,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         }
         n2_s[row] = n2;
         store_x_images<DH>(xh, xl, rowv, row);
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) st4(&xrow_s[row][4 * c], make_float4(rowv[4 * c], rowv[4 * c + 1], rowv[4 * c + 2], rowv[4 * c + 3]));
       } else if (part == 1) {
         if (pass != 1) {  // [v_hi | 1 | 0 | v_lo]
 #pragma unroll
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           *reinterpret_cast<uint4*>(av_side + 2 * kTokCh + rowoff) = make_uint4(valid ? 0x00003F80u : 0u, 0u, 0u, 0u);
         }
       }
+      }  // !skip
       if (skip && lone) {
         // feature rows of the lone tokens on all 16 warps: warp = (feature quarter, pair side, q|k).  Raw projections
         // and the quarter's maximum go to shared memory; the exponentials follow after the barrier.
@@ -749,7 +756,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         if (part == 0 && valid) {
           float dy[DH], dxr[DH];
 #pragma unroll
-          for (int d = 0; d < DH; ++d) dy[d] = (favor ? acc[d] - rowv[d] * acc[DH] : acc[d]) * p.prescale;
+          for (int d = 0; d < DH; ++d) dy[d] = (favor ? acc[d] - xrow_s[row][d] * acc[DH] : acc[d]) * p.prescale;
           const T* xraw = qkv + qkv_off(b, n, which, h, N, H, DH);
           prologue_row_bwd<T, DH>(dy, dxr, p.rot, p.ta, p.tb, h, n, N, dg_slot ? dg_slot + (size_t)side * N * DH : nullptr, xraw);
           T* dst = dqkv + qkv_off(b, n, which, h, N, H, DH);
@@ -813,7 +820,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           for (int c = 0; c < DH / 8; ++c) {
             float ch[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ch[e] = rowv[8 * c + e] * r;
+            for (int e = 0; e < 8; ++e) ch[e] = reinterpret_cast<const float*>(o_raw)[row * DH + 8 * c + e] * r;
             store_split8(av_side, av_side + 4 * kTokCh, c * kTokCh + rowoff, ch);
           }
           const float a16 = valid ? -dot * r : 0.f;
