@@ -241,17 +241,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
 
   const int ntiles = (p.R + 127) / 128;
   bool first = true;
+  float na[8], nx[8], ndy[8];  // rows of the next tile, in flight while this one is processed
+  auto load_rows = [&](int tile) {
+    const int rr = tile * 128 + row;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) na[i] = nx[i] = ndy[i] = 0.f;
+    if (tile < ntiles && rr < p.R) {
+      ld8(p.a + (size_t)rr * C + c0, na);
+      ld8(p.x + (size_t)rr * C + c0, nx);
+      ld8(p.dy + (size_t)rr * C + c0, ndy);
+    }
+  };
+  load_rows(blockIdx.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r = tile * 128 + row;
     const bool valid = r < p.R;
     float a[8], x[8], dy[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = x[i] = dy[i] = 0.f;
-    if (valid) {
-      ld8(p.a + (size_t)r * C + c0, a);
-      ld8(p.x + (size_t)r * C + c0, x);
-      ld8(p.dy + (size_t)r * C + c0, dy);
-    }
+    for (int i = 0; i < 8; ++i) { a[i] = na[i]; x[i] = nx[i]; dy[i] = ndy[i]; }
     if (!first) {  // the previous tile's token reductions still read the images
       mbar_wait(&bar_w, ph_w);
       ph_w ^= 1;
@@ -272,6 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
       tc_row_product3(cx, COL_G, IMG_DO, IMG_DO + 4, IMG_DO + 8, 2, W2B, 256, 128, 512, x192, x128, x64);  // dh raw -> [0,192)
       commit(&bar_g);
     }
+    load_rows(tile + gridDim.x);
     wait_g();
     float dhr[16];
     {
@@ -693,25 +701,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_bwd_tc_kernel(const LnQk
   const uint32_t w80 = make_idesc(FMT_BF16, 128, 80, true, true), w48 = make_idesc(FMT_BF16, 128, 48, true, true);
   const int ntiles = (p.R + 127) / 128;
   bool first = true;
+  float nx[8], ndq[24];  // rows of the next tile, in flight while this one is processed
+  auto load_rows = [&](int tile) {
+    const int rr = tile * 128 + row;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nx[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) ndq[i] = 0.f;
+    if (tile < ntiles && rr < p.R) {
+      ld8(p.x + (size_t)rr * C + c0, nx);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float t[8];
+        ld8(p.dqkv + (size_t)rr * QKV + q0 + 8 * k, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ndq[8 * k + i] = t[i];
+      }
+    }
+  };
+  load_rows(blockIdx.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r = tile * 128 + row;
     const bool valid = r < p.R;
     float x[8], dres[8], dq[24];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = dres[i] = 0.f;
+    for (int i = 0; i < 8; ++i) { x[i] = nx[i]; dres[i] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < 24; ++i) dq[i] = 0.f;
-    if (valid) {
-      ld8(p.x + (size_t)r * C + c0, x);
-      if (p.dres) ld8(p.dres + (size_t)r * C + c0, dres);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float t[8];
-        ld8(p.dqkv + (size_t)r * QKV + q0 + 8 * k, t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dq[8 * k + i] = t[i];
-      }
-    }
+    for (int i = 0; i < 24; ++i) dq[i] = ndq[i];
+    if (valid && p.dres) ld8(p.dres + (size_t)r * C + c0, dres);
     if (!first) {  // the previous tile's token reduction still reads the images
       mbar_wait(&bar_w, ph_w);
       ph_w ^= 1;
@@ -745,6 +762,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_bwd_tc_kernel(const LnQk
       tc_token_reduction(cx, B_COL_ACC, B_DQ, B_DQ + 12, B_N, w80, w48, first);                    // dW_qkv | db_qkv
       commit(&bar_w);
     }
+    load_rows(tile + gridDim.x);
     mbar_wait(&bar_g, ph_g);
     ph_g ^= 1;
     fence_after_sync();
