@@ -154,6 +154,7 @@ __device__ __forceinline__ void ln_stats4(const float (&v)[8], float (*ex_a)[128
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;           \
   const uint32_t rowoff = (uint32_t)(row >> 3) * 128 + (row & 7) * 16;                      \
   uint8_t* const img = smem;                                                                \
+  (void)ex_a; (void)ex_b;                                                                   \
   if (warp == 0) tmem_alloc(&tmem_base_s, NCOLS)
 
 // ---- backward of the MLP half ----------------------------------------------------------------------------------------------
@@ -829,6 +830,204 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_bwd_tc_kernel(const LnQk
   if (warp == 0) tmem_dealloc(tm, 256);
 }
 
+
+// ---- patch embedding + CLS + position embedding (base_vit.py:190-223) for 4x4 patches, <= 4 channels ------------------------
+// x[b, 0] = cls + pos[0] ; x[b, 1+p] = patch(b, p) W^T + bias + pos[1+p].  A tile is 128 consecutive tokens of [B*N];
+// thread (row, part) gathers the 16 pixels of channel `part` of its token's patch (four 16-byte loads), which are exactly
+// the k = part*16 .. +15 columns of the patch row (k = c P^2 + i P + j), so the patch image needs no transposition.
+struct EmbedTcArgs {
+  const float* img; const float* w; const float* b; const float* cls; const float* pos;
+  float* out;
+  const float* dout; float* part;  // backward: per-CTA partials [32*PD | 32 | 32 | N*32] = dW | db | dcls | dpos
+  int B, Cin, S, G, N, PD;
+};
+constexpr uint32_t E_A = 0, E_END = 24, E_W = E_END * CH, E_SMEM = E_W + 8 * 1536;  // patches [hi 8 | lo 8 | lo2 8] ; W (K padded to 64): 60 KB
+
+__device__ __forceinline__ void gather_patch16(const EmbedTcArgs& p, long t, int part, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  if (t >= (long)p.B * p.N || part >= p.Cin) return;
+  const int b = (int)(t / p.N), n = (int)(t - (long)b * p.N);
+  if (n == 0) return;
+  const int gy = (n - 1) / p.G, gx = (n - 1) - gy * p.G;
+  const float* src = p.img + (((size_t)b * p.Cin + part) * p.S + gy * 4) * p.S + gx * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = ld4(src + (size_t)i * p.S);
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) embed_fwd_tc_kernel(const EmbedTcArgs p) {
+  ERV_TC_PROLOGUE(128);
+  __shared__ __align__(8) uint64_t bar_g;
+  for (uint32_t i = tid; i < E_SMEM / 16; i += kTcThreads) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bar_g, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  stage_w_fwd3(smem + E_W, p.w, 0, C, p.PD);  // columns k >= PD stay zero
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const TcCtx cx{tmem_base_s, smem_u32(smem)};
+  const uint32_t tm = cx.tm, lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t ph_g = 0;
+  const int c0 = part * 8;
+  float bias[8], cls[8];
+  ld8(p.b + c0, bias); ld8(p.cls + c0, cls);
+  const uint32_t f96 = make_idesc(FMT_BF16, 128, 96, false, false), f64 = make_idesc(FMT_BF16, 128, 64, false, false);
+  const uint32_t f32 = make_idesc(FMT_BF16, 128, 32, false, false);
+  const long total = (long)p.B * p.N;
+  const long ntiles = (total + 127) / 128;
+  float nv[16];
+  gather_patch16(p, (long)blockIdx.x * 128 + row, part, nv);
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long t = tile * 128 + row;
+    {
+      float h8[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h8[i] = nv[8 * hh + i];
+        store_split8_3(img + E_A * CH, img + (E_A + 8) * CH, img + (E_A + 16) * CH, (uint32_t)(2 * part + hh) * CH + rowoff, h8);
+      }
+    }
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      tc_row_product3(cx, 0, E_A, E_A + 8, E_A + 16, (p.PD + 15) / 16, E_W, 2 * 1536, 1536, 128, f96, f64, f32);
+      commit(&bar_g);
+    }
+    gather_patch16(p, (tile + gridDim.x) * 128 + row, part, nv);
+    mbar_wait(&bar_g, ph_g);
+    ph_g ^= 1;
+    fence_after_sync();
+    float o[8];
+    tmem_sum3(tm + lane_off + c0, 32, o);
+    if (t < total) {
+      const int n = (int)(t % p.N);
+      float pos[8];
+      ld8(p.pos + (size_t)n * C + c0, pos);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (n == 0 ? cls[i] : o[i] + bias[i]) + pos[i];
+      st8(p.out + (size_t)t * C + c0, o);
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 128);
+}
+
+// backward: dW | db (token reduction dout^T [patch | 1] accumulated in TMEM), dpos / dcls (per-CTA shared-memory sums)
+constexpr uint32_t EB_DO = 0, EB_P = 8, EB_END = 26, EB_SMEM = EB_END * CH;  // dout [hi 4 | lo 4] ; patches [hi 8 | 1 | 0 | lo 8]: 52 KB
+
+__global__ void __launch_bounds__(kTcThreads, 1) embed_bwd_tc_kernel(const EmbedTcArgs p) {
+  ERV_TC_PROLOGUE(256);
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ float dpos_s[128 * C];  // N <= 128 rows
+  for (uint32_t i = tid; i < EB_SMEM / 16; i += kTcThreads) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128 * C; i += kTcThreads) dpos_s[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (part == 0) *reinterpret_cast<uint16_t*>(img + (EB_P + 8) * CH + rowoff) = 0x3F80;  // ones column
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const TcCtx cx{tmem_base_s, smem_u32(smem)};
+  const uint32_t tm = cx.tm, lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t ph_w = 0;
+  const int c0 = part * 8;
+  const uint32_t w144 = make_idesc(FMT_BF16, 128, 144, true, true), w80 = make_idesc(FMT_BF16, 128, 80, true, true);
+  const long total = (long)p.B * p.N;
+  const long ntiles = (total + 127) / 128;
+  bool first = true;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long t = tile * 128 + row;
+    const bool valid = t < total;
+    const int n = valid ? (int)(t % p.N) : 0;
+    float d[8], v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+    if (valid) ld8(p.dout + (size_t)t * C + c0, d);
+    gather_patch16(p, t, part, v);
+    if (!first) {  // the previous tile's reduction still reads the images
+      mbar_wait(&bar_w, ph_w);
+      ph_w ^= 1;
+      fence_after_sync();
+    }
+    {
+      float dz[8];  // CLS rows take no part in dW / db
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = (valid && n > 0) ? d[i] : 0.f;
+      store_split8(img + EB_DO * CH, img + (EB_DO + 4) * CH, (uint32_t)part * CH + rowoff, dz);
+      float h8[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h8[i] = v[8 * hh + i];
+        store_split8(img + EB_P * CH, img + (EB_P + 10) * CH, (uint32_t)(2 * part + hh) * CH + rowoff, h8);
+      }
+    }
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      tc_token_reduction(cx, 0, EB_DO, EB_DO + 4, EB_P, w144, w80, first);
+      commit(&bar_w);
+    }
+    // dpos: rows of a tile that share a position are N apart; add them in groups of N consecutive rows (deterministic)
+    for (int g0 = 0; g0 < 128; g0 += p.N) {
+      if (valid && row >= g0 && row < g0 + p.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dpos_s[n * C + c0 + i] += d[i];
+      }
+      __syncthreads();
+    }
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(&bar_w, ph_w);
+    ph_w ^= 1;
+    fence_after_sync();
+  }
+  const int P = C * p.PD + 2 * C + p.N * C;
+  float* part_out = p.part + (size_t)blockIdx.x * P;
+  if (first) {
+    for (int i = tid; i < P; i += kTcThreads) part_out[i] = 0.f;
+  } else {
+    if (part == 0 && warp == 0) {  // rows o < 32: dW[o][k] = D[k] + D[80 + k], db[o] = D[64]
+      float a[16], l[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tmem_ld16(tm + lane_off + 16 * q, a);
+        tmem_ld16(tm + lane_off + 80 + 16 * q, l);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (16 * q + i < p.PD) part_out[row * p.PD + 16 * q + i] = a[i] + l[i];
+      }
+      tmem_ld16(tm + lane_off + 64, a);
+      part_out[C * p.PD + row] = a[0];
+    }
+    for (int i = tid; i < C; i += kTcThreads) part_out[C * p.PD + C + i] = dpos_s[i];           // dcls = row 0
+    for (int i = tid; i < p.N * C; i += kTcThreads) part_out[C * p.PD + 2 * C + i] = dpos_s[i];  // dpos
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 256);
+}
+
 }  // namespace blk
 }  // namespace erv
 
@@ -883,6 +1082,39 @@ int launch_ln_qkv_tc(bool bwd, const float* x, const float* ln_w, const float* l
   ERV_LAUNCH_CHECK();
   if (grid_out) *grid_out = grid;
   return ERV_OK;
+}
+
+bool embed_tc_eligible(int Cin, int P, int N) { return mlp_bwd_tc_enabled() && P == 4 && Cin >= 1 && Cin <= 4 && N <= 128; }
+static int embed_tc_grid(int B, int N) {
+  const long tiles = ((long)B * N + 127) / 128;
+  return (int)(tiles < kNumSMs ? tiles : kNumSMs);
+}
+size_t embed_tc_bwd_workspace(int B, int Cin, int N) {
+  return align_up((size_t)embed_tc_grid(B, N) * (C * Cin * 16 + 2 * C + N * C) * sizeof(float), 256);
+}
+int launch_embed_fwd_tc(const float* images, const float* w, const float* b, const float* cls, const float* pos, float* out,
+                        int B, int Cin, int S, cudaStream_t st) {
+  EmbedTcArgs a{};
+  a.img = images; a.w = w; a.b = b; a.cls = cls; a.pos = pos; a.out = out;
+  a.B = B; a.Cin = Cin; a.S = S; a.G = S / 4; a.N = a.G * a.G + 1; a.PD = Cin * 16;
+  ERV_CUDA(allow_smem(embed_fwd_tc_kernel, E_SMEM));
+  embed_fwd_tc_kernel<<<embed_tc_grid(B, a.N), kTcThreads, E_SMEM, st>>>(a);
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
+// gradients are ADDED to dw [32][PD], db [32], dcls [32], dpos [N][32] (the caller zeroes them when it wants plain values)
+int launch_embed_bwd_tc(const float* images, const float* dout, float* dw, float* db, float* dcls, float* dpos, int B, int Cin,
+                        int S, float* workspace, cudaStream_t st) {
+  EmbedTcArgs a{};
+  a.img = images; a.dout = dout; a.part = workspace;
+  a.B = B; a.Cin = Cin; a.S = S; a.G = S / 4; a.N = a.G * a.G + 1; a.PD = Cin * 16;
+  const int grid = embed_tc_grid(B, a.N);
+  ERV_CUDA(allow_smem(embed_bwd_tc_kernel, EB_SMEM));
+  embed_bwd_tc_kernel<<<grid, kTcThreads, EB_SMEM, st>>>(a);
+  ERV_LAUNCH_CHECK();
+  float* dst[4] = {dw, db, dcls, dpos};
+  const int seg[5] = {0, C * a.PD, C * a.PD + C, C * a.PD + 2 * C, C * a.PD + 2 * C + a.N * C};
+  return launch_sum(workspace, nullptr, grid, seg[4], dst, seg, 4, st);
 }
 }  // namespace blk
 }  // namespace erv

@@ -213,6 +213,17 @@ static int fill_embed(EmbedArgs& a, const char* fn, int B, int Cin, int S, int P
 }  // namespace eh
 }  // namespace erv
 
+namespace erv {
+namespace blk {  // tcgen05 versions for 4x4 patches (erv_block_tc.cu)
+bool embed_tc_eligible(int Cin, int P, int N);
+size_t embed_tc_bwd_workspace(int B, int Cin, int N);
+int launch_embed_fwd_tc(const float* images, const float* w, const float* b, const float* cls, const float* pos, float* out,
+                        int B, int Cin, int S, cudaStream_t st);
+int launch_embed_bwd_tc(const float* images, const float* dout, float* dw, float* db, float* dcls, float* dpos, int B, int Cin,
+                        int S, float* workspace, cudaStream_t st);
+}  // namespace blk
+}  // namespace erv
+
 using namespace erv;
 using namespace erv::eh;
 
@@ -224,6 +235,7 @@ extern "C" int erv_embed_fwd(const float* images, const float* w, const float* b
   EmbedArgs a{};
   int rc = fill_embed(a, "erv_embed_fwd", B, Cin, S, P);
   if (rc) return rc;
+  if (blk::embed_tc_eligible(Cin, P, a.N)) return blk::launch_embed_fwd_tc(images, w, b, cls, pos, out, B, Cin, S, (cudaStream_t)stream);
   a.img = images; a.w = w; a.b = b; a.cls = cls; a.pos = pos; a.out = out;
   const size_t smem = (size_t)(a.PD * C + 8 * a.PD) * sizeof(float);
   ERV_CUDA(allow_smem(embed_fwd_kernel, smem));
@@ -242,7 +254,9 @@ static int embed_grid(int B, int N) {
 extern "C" size_t erv_embed_bwd_workspace(int B, int Cin, int S, int P) {
   if (B <= 0 || P <= 0 || S % P) return 0;
   const int G = S / P, N = G * G + 1, PD = Cin * P * P;
-  return align_up((size_t)embed_grid(B, N) * C * PD * sizeof(float), 256) + align_up((size_t)N * C * sizeof(float), 256);
+  const size_t fma = align_up((size_t)embed_grid(B, N) * C * PD * sizeof(float), 256) + align_up((size_t)N * C * sizeof(float), 256);
+  const size_t tc = blk::embed_tc_eligible(Cin, P, N) ? blk::embed_tc_bwd_workspace(B, Cin, N) : 0;
+  return fma > tc ? fma : tc;
 }
 
 // dw [32][PD], db [32], dcls [32], dpos [N][32]; accumulate != 0 adds to the existing contents (fused accumulation into .grad)
@@ -255,6 +269,15 @@ extern "C" int erv_embed_bwd(const float* images, const float* dout, float* dw, 
   if (rc) return rc;
   if (workspace_bytes < erv_embed_bwd_workspace(B, Cin, S, P)) { set_error("erv_embed_bwd: workspace too small"); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (blk::embed_tc_eligible(Cin, P, a.N)) {
+    if (!accumulate) {
+      ERV_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * a.PD * sizeof(float), st));
+      ERV_CUDA(cudaMemsetAsync(db, 0, C * sizeof(float), st));
+      ERV_CUDA(cudaMemsetAsync(dcls, 0, C * sizeof(float), st));
+      ERV_CUDA(cudaMemsetAsync(dpos, 0, (size_t)a.N * C * sizeof(float), st));
+    }
+    return blk::launch_embed_bwd_tc(images, dout, dw, db, dcls, dpos, B, Cin, S, (float*)workspace, st);
+  }
   const int grid = embed_grid(B, a.N);
   a.img = images; a.dout = dout; a.part = (float*)workspace;
   float* tmp = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)grid * C * a.PD * sizeof(float), 256));

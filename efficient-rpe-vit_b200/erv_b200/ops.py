@@ -446,9 +446,14 @@ class _LayerNorm(torch.autograd.Function):
 
 # ---- fused block kernels (dim 32, MLP width 64): LayerNorm1 + qkv ; proj + residual + LayerNorm2 + MLP + residual ------
 FUSED_BLOCK = True  # False: the block runs op by op (Linear / LayerNorm / GELU / Dropout modules)
-# The fused patch-embedding kernels (csrc/erv_embed_head.cu) are correct but, as plain FMA kernels with per-token gathers,
-# not yet faster than the library chain they replace (168 us for the weight gradient at config 2): off by default.
-FUSED_EMBED = False
+# Fused patch embedding + CLS + positions: tcgen05 kernels for 4x4 patches (csrc/erv_block_tc.cu), plain FMA kernels with
+# per-token gathers otherwise (csrc/erv_embed_head.cu; slower than the library chain they replace, so only used on request).
+FUSED_EMBED = True
+
+
+def embed_fast(cin: int, patch: int, n_tokens: int) -> bool:
+    """True when the tcgen05 embedding kernels cover this geometry."""
+    return patch == 4 and 1 <= cin <= 4 and n_tokens <= 128
 # True (set by erv_b200.train.Trainer): the fused backward kernels add parameter gradients straight into the existing
 # fp32 `.grad` buffers and return None to autograd, which saves one accumulation kernel per parameter.  Only valid when
 # nothing else looks at the per-call gradients (no hooks, no create_graph); off by default.
@@ -595,7 +600,7 @@ class _Embed(torch.autograd.Function):
         out = torch.empty(bsz, n, w.shape[0], device=images.device, dtype=torch.float32)
         C.check(C.load().erv_embed_fwd(C.ptr(images), C.ptr(w), C.ptr(b), C.ptr(cls), C.ptr(pos), C.ptr(out), bsz, cin, s, patch,
                                        C.stream()), "embed")
-        ctx.save_for_backward(images, w, b, cls, pos)
+        ctx.save_for_backward(images, w, b, cls, pos)  # cls [1,1,dim], pos [1,N,dim]: the parameters themselves
         ctx.patch = patch
         return out
 

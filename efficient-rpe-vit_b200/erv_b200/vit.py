@@ -117,13 +117,14 @@ class BaseViT(nn.Module):
 
     def features(self, x: torch.Tensor) -> torch.Tensor:
         """images -> token features after the last block [B, N, dim]."""
-        if ops.FUSED_EMBED and self._fused_ends(x):
+        if (ops.FUSED_EMBED and self._fused_ends(x)
+                and (ops.embed_fast(self.in_channels, self.patch_size, self.num_patches + 1) or ops.FUSED_EMBED == "always")):
             b, c, h, w = x.shape
             assert c == self.in_channels, f"Expected {self.in_channels} channels, got {c}"
             assert h == self.image_size and w == self.image_size, \
                 f"Expected {self.image_size}x{self.image_size} images, got {h}x{w}"
-            x = ops.embed(x, self.patch_embedding.weight, self.patch_embedding.bias, self.cls_token.reshape(-1),
-                          self.pos_embedding.reshape(-1, self.dim), self.patch_size)
+            x = ops.embed(x, self.patch_embedding.weight, self.patch_embedding.bias, self.cls_token, self.pos_embedding,
+                          self.patch_size)
         else:
             x = self.patch_embedding(self.patchify(x))
             x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding

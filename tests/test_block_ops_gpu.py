@@ -212,7 +212,7 @@ def test_fused_embed_and_head_loss_match_library_path(cfg, patch, bsz, monkeypat
     res = []
     for fused in (True, False):
         monkeypatch.setattr(ops, "FUSED_BLOCK", fused)
-        monkeypatch.setattr(ops, "FUSED_EMBED", fused)
+        monkeypatch.setattr(ops, "FUSED_EMBED", "always" if fused else False)
         model.zero_grad()
         loss = model.loss(img, lab)
         loss.backward()
