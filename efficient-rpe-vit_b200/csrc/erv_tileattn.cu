@@ -42,8 +42,10 @@ struct TileArgs {
   int B, N, H, KD, ldr; // KD = inner dim padded to 8, ldr = row stride of q/k rows
   float scale, dropout_p;
   uint64_t seed;
+  const unsigned long long* seed_dev;  // optional device-resident seed (xor-ed in): new masks on every CUDA-graph replay
 };
 
+__device__ __forceinline__ uint64_t eff_seed(const TileArgs& p) { return p.seed ^ (p.seed_dev ? __ldg(p.seed_dev) : 0ull); }
 // counter-based keep mask: uniform in [0,1) from (seed, pair, i, j)
 __device__ __forceinline__ float rng_uniform(uint64_t seed, uint32_t pair, uint32_t i, uint32_t j) {
   uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * ((uint64_t)pair + 1));
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) tile_fwd_kernel(const TileArgs p) {
           float pv = (m_new == -INFINITY) ? 0.f : expf(s[r][c] - m_new);
           rs += pv;
           if (p.dropout_p > 0.f)
-            pv = (rng_uniform(p.seed, pair, i, j0 + jl) >= p.dropout_p) ? pv * keep_scale : 0.f;
+            pv = (rng_uniform(eff_seed(p), pair, i, j0 + jl) >= p.dropout_p) ? pv * keep_scale : 0.f;
           Ps[il * LDP + jl] = pv;
         }
         rs = half_sum(rs);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(256) tile_fwd_kernel(const TileArgs p) {
           float v = s[r][c] * p.scale;
           if (p.mask && p.mask[((size_t)b * N + i) * N + j] == 0) v = -INFINITY;
           float pv = expf(v - lse);
-          if (p.dropout_p > 0.f) pv = (rng_uniform(p.seed, pair, i, j) >= p.dropout_p) ? pv * keep_scale : 0.f;
+          if (p.dropout_p > 0.f) pv = (rng_uniform(eff_seed(p), pair, i, j) >= p.dropout_p) ? pv * keep_scale : 0.f;
           p.attn_out[((size_t)pair * N + i) * N + j] = pv;
         }
       }
@@ -335,7 +337,7 @@ __device__ __forceinline__ void bwd_tile_weights(const TileArgs& p, float (&s)[4
           if (p.mask && p.mask[((size_t)b * N + i) * N + j] == 0) v = -INFINITY;
           const float pr = expf(v - rowA[il]);            // rowA = lse_i
           float keep = 1.f;
-          if (p.dropout_p > 0.f) keep = (rng_uniform(p.seed, pair, i, j) >= p.dropout_p) ? keep_scale : 0.f;
+          if (p.dropout_p > 0.f) keep = (rng_uniform(eff_seed(p), pair, i, j) >= p.dropout_p) ? keep_scale : 0.f;
           w = pr * keep;                                  // Pd
           g = pr * (dp[r][c] * keep - rowB[il]) * p.scale;  // rowB = D_i
         }
@@ -750,7 +752,8 @@ extern "C" size_t erv_softmax_attention_workspace(int B, int N, int H, int head_
 extern "C" int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_out, float* attn_out,
                                          const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
                                          const float* tab_a, const float* tab_b, float dropout_p, uint64_t seed,
-                                         int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+                                         const long long* seed_dev, int dtype, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   const char* fn = "erv_softmax_attention_fwd";
   int rc = check_shape(fn, B, N, H, head_dim, dtype);
   if (rc) return rc;
@@ -772,6 +775,7 @@ extern "C" int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_
   a.qkv = qkv; a.out = out; a.stat = lse_out; a.attn_out = attn_out; a.mask = mask;
   a.B = B; a.N = N; a.H = H; a.KD = head_dim; a.ldr = head_dim;
   a.scale = (float)pow((double)head_dim, -0.5); a.dropout_p = dropout_p; a.seed = seed;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   return dtype == ERV_F32 ? tile_forward<float, MODE_SOFTMAX>(a, head_dim, st)
                           : tile_forward<__nv_bfloat16, MODE_SOFTMAX>(a, head_dim, st);
 }
@@ -779,8 +783,8 @@ extern "C" int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_
 extern "C" int erv_softmax_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout,
                                          void* dqkv, const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
                                          const float* tab_a, const float* tab_b, float* dg_part, float dropout_p,
-                                         uint64_t seed, int dtype, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         uint64_t seed, const long long* seed_dev, int dtype, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
   const char* fn = "erv_softmax_attention_bwd";
   int rc = check_shape(fn, B, N, H, head_dim, dtype);
   if (rc) return rc;
@@ -805,6 +809,7 @@ extern "C" int erv_softmax_attention_bwd(const void* qkv, const void* out, const
   a.qkv = qkv; a.dqkv = dqkv; a.out = const_cast<void*>(out); a.dout = dout; a.stat = const_cast<float*>(lse);
   a.mask = mask; a.B = B; a.N = N; a.H = H; a.KD = head_dim; a.ldr = head_dim;
   a.scale = (float)pow((double)head_dim, -0.5); a.dropout_p = dropout_p; a.seed = seed;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   rc = dtype == ERV_F32 ? tile_backward<float, MODE_SOFTMAX>(a, head_dim, st)
                         : tile_backward<__nv_bfloat16, MODE_SOFTMAX>(a, head_dim, st);
   if (rc) return rc;

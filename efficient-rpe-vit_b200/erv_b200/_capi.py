@@ -58,8 +58,8 @@ SIGNATURES = {
     "erv_block_mlp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P, _Z, _P]),
     "erv_kerple_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_kerple_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
-    "erv_softmax_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, c_uint64, _I, _P, _Z, _P]),
-    "erv_softmax_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, c_uint64, _I, _P, _Z, _P]),
+    "erv_softmax_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, c_uint64, _P, _I, _P, _Z, _P]),
+    "erv_softmax_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, c_uint64, _P, _I, _P, _Z, _P]),
     "erv_toeplitz_matmul_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_toeplitz_matmul_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_adam_step": (c_int, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _I, _F, c_int64, _P, _P]),

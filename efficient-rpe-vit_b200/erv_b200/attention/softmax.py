@@ -30,8 +30,9 @@ class SoftmaxAttention(BaseAttention):
         """Packed qkv [B, N, 3C] -> attention output [B, N, C] before the output projection (and the weights)."""
         rot, gtab, ta, tb = rotation_args(rpe, x_shape, self.heads, self.head_dim)
         p = self.attn_dropout.p if self.training else 0.0
+        # the seed lives on the device (a counter advanced by every call), so CUDA-graph replays draw new masks
         out, attn = ops.softmax_attention(qkv, self.heads, rot, gtab, ta, tb, mask, p,
-                                          ops.next_seed() if p > 0 else 0, return_attention)
+                                          ops.dropout_seed(qkv.device) if p > 0 else 0, return_attention)
         return (out, attn) if return_attention else out
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, rpe: Optional[nn.Module] = None,

@@ -295,12 +295,14 @@ class _SoftmaxAttention(torch.autograd.Function):
         attn = torch.empty(b, heads, n, n, device=qkv.device, dtype=torch.float32) if want_attn else None
         nbytes = lib.erv_softmax_attention_workspace(b, n, heads, dh, rot, 0)
         ws = C.workspace(nbytes, qkv.device)
+        seed_dev = seed if torch.is_tensor(seed) else None  # device-resident seed (ops.dropout_seed): graph-replay safe
+        seed = 0 if seed_dev is not None else int(seed)
         with _timed("softmax_attention_fwd"):
             C.check(lib.erv_softmax_attention_fwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(attn), C.ptr(mask8), b, n, heads,
-                                                  dh, rot, C.ptr(ta), C.ptr(tb), float(dropout_p), seed, C.dtype_code(qkv),
-                                                  C.ptr(ws), nbytes, C.stream()), "softmax_attention")
+                                                  dh, rot, C.ptr(ta), C.ptr(tb), float(dropout_p), seed, C.ptr(seed_dev),
+                                                  C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()), "softmax_attention")
         ctx.meta = (b, n, heads, dh, rot, float(dropout_p), seed)
-        ctx.save_for_backward(qkv, out, lse, ta, tb, mask8)
+        ctx.save_for_backward(qkv, out, lse, ta, tb, mask8, seed_dev)
         if want_attn:
             ctx.mark_non_differentiable(attn)
             return out, attn
@@ -309,7 +311,7 @@ class _SoftmaxAttention(torch.autograd.Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout, _dattn):
-        qkv, out, lse, ta, tb, mask8 = ctx.saved_tensors
+        qkv, out, lse, ta, tb, mask8, seed_dev = ctx.saved_tensors
         b, n, heads, dh, rot, p, seed = ctx.meta
         lib = C.load()
         dout = dout.to(qkv.dtype).contiguous()
@@ -323,7 +325,8 @@ class _SoftmaxAttention(torch.autograd.Function):
         with _timed("softmax_attention_bwd"):
             C.check(lib.erv_softmax_attention_bwd(C.ptr(qkv), C.ptr(out), C.ptr(lse), C.ptr(dout), C.ptr(dqkv), C.ptr(mask8),
                                                   b, n, heads, dh, rot, C.ptr(ta), C.ptr(tb), C.ptr(dg_part), p, seed,
-                                                  C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()), "softmax_attention_bwd")
+                                                  C.ptr(seed_dev), C.dtype_code(qkv), C.ptr(ws), nbytes, C.stream()),
+                    "softmax_attention_bwd")
         dgtab = dg_part.sum(dim=1) if (dg_part is not None and ctx.needs_input_grad[1]) else None
         return dqkv, dgtab, None, None, None, None, None, None, None, None
 

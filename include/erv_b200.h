@@ -192,18 +192,20 @@ int erv_kerple_attention_bwd(const void* qkv, const void* out, const float* den,
 /* Softmax attention (softmax.py:86-115): out = dropout(softmax(rot(q) rot(k)^T / sqrt(Dh) + mask)) v.
  * mask: optional uint8 [B, N, N] (0 = masked, softmax.py:104-108), may be NULL.
  * dropout_p in [0,1): attention-probability dropout (softmax.py:112) from a counter-based generator
- * keyed by (seed, b, h, i, j) so the backward regenerates it.
+ * keyed by (seed ^ *seed_dev, b, h, i, j) so the backward regenerates it; seed_dev (optional, may be NULL) is a
+ * device-resident 64-bit value, so a captured CUDA graph draws new masks on every replay.
  * lse_out [B, H, N] (log-sum-exp, saved for backward).  attn_out: optional [B, H, N, N] fp32 dump of the
  * (post-dropout) probabilities for return_attention=True (softmax.py:122-123), may be NULL. */
 int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_out, float* attn_out,
                               const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
                               const float* tab_a, const float* tab_b, float dropout_p, uint64_t seed,
-                              int dtype, void* workspace, size_t workspace_bytes, void* stream);
+                              const long long* seed_dev, int dtype, void* workspace, size_t workspace_bytes,
+                              void* stream);
 int erv_softmax_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout,
                               void* dqkv, const uint8_t* mask, int B, int N, int H, int head_dim, int rot,
                               const float* tab_a, const float* tab_b, float* dg_part, float dropout_p,
-                              uint64_t seed, int dtype, void* workspace, size_t workspace_bytes,
-                              void* stream);
+                              uint64_t seed, const long long* seed_dev, int dtype, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ---- Toeplitz product -------------------------------------------------------------------- */
 

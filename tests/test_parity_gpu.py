@@ -321,3 +321,32 @@ def test_training_steps_are_stable():
             loss.backward()
             opt.step()
         assert torch.isfinite(loss) and float(loss) < 100
+
+
+def test_softmax_dropout_draws_new_masks_on_graph_replay():
+    """The attention-dropout seed is device resident: a captured CUDA graph must not replay the same mask."""
+    from erv_b200 import SoftmaxAttention, ops
+    torch.manual_seed(0)
+    attn = SoftmaxAttention(32, 2, dropout=0.3).to(DEV).train()
+    x = torch.randn(4, 17, 32, device=DEV)
+    with torch.no_grad():
+        qkv = attn.qkv(x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            attn.core(qkv, x.shape, None)  # warm-up: creates the per-device seed state outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = attn.core(qkv, x.shape, None)
+        g.replay()
+        a = out.clone()
+        g.replay()
+        b = out.clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    # a fixed device seed reproduces the mask, forward and backward
+    seed = torch.tensor([77], dtype=torch.int64, device=DEV)
+    o1, _ = ops.softmax_attention(qkv, 2, dropout_p=0.3, seed=seed)
+    o2, _ = ops.softmax_attention(qkv, 2, dropout_p=0.3, seed=seed)
+    assert torch.equal(o1, o2)
