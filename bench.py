@@ -26,6 +26,8 @@ for p in (ROOT, os.path.join(ROOT, "efficient-rpe-vit_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (the result is ONE JSON line)
+
 import torch  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
