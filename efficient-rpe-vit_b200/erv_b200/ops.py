@@ -562,6 +562,7 @@ class _BlockMlp(torch.autograd.Function):
                                            float(p_drop), C.ptr(seed), int(salt), C.stream()), "block_mlp")
         ctx.save_for_backward(a2, x2, seed, *params)
         ctx.meta = (x.shape, float(eps), float(p_drop), int(salt), mlp_dim)
+        ctx.a_dtype = a.dtype
         return y.reshape(x.shape)
 
     @staticmethod
@@ -579,13 +580,14 @@ class _BlockMlp(torch.autograd.Function):
         C.check(lib.erv_block_mlp_bwd(C.ptr(a2), C.ptr(x2), C.ptr(dy2), _param_array(params), C.ptr(da), C.ptr(dx1), C.ptr(dpar),
                                       _ptr_array(tgt) if tgt else None, rows, dim, mlp_dim, eps, p_drop, C.ptr(seed), salt,
                                       C.ptr(ws), nbytes, C.stream()), "block_mlp_bwd")
+        da = da.reshape(shape).to(ctx.a_dtype)
         if tgt:
-            return (da.reshape(shape), dx1.reshape(shape), *([None] * 12))
+            return (da, dx1.reshape(shape), *([None] * 12))
         o, grads = 0, []
         for t in params:  # dparams follows the parameter order
             grads.append(dpar[o:o + t.numel()].view(t.shape))
             o += t.numel()
-        return (da.reshape(shape), dx1.reshape(shape), *grads, None, None, None, None)
+        return (da, dx1.reshape(shape), *grads, None, None, None, None)
 
 
 def block_mlp(a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, p_drop=0.0, seed=None, salt=0):

@@ -47,8 +47,10 @@ class Trainer:
         try:
             if self.autocast_dtype is not None:
                 with torch.autocast("cuda", dtype=self.autocast_dtype):
-                    logits = self.model(images)
-                loss = F.cross_entropy(logits.float(), labels)
+                    if hasattr(self.model, "loss"):
+                        loss = self.model.loss(images, labels)
+                    else:
+                        loss = F.cross_entropy(self.model(images).float(), labels)
             elif hasattr(self.model, "loss"):
                 loss = self.model.loss(images, labels)  # head + criterion fused when the model supports it
             else:

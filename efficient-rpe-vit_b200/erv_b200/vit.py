@@ -13,6 +13,11 @@ from . import ops
 from .nn import LayerNorm, Linear
 
 
+def _autocast_ok() -> bool:
+    """No autocast, or bf16 autocast on CUDA (the fused fp32 kernels then feed the attention core bf16 operands)."""
+    return (not torch.is_autocast_enabled()) or torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
 class UnifiedTransformerBlock(nn.Module):
     """x + attn(norm1(x), rpe) ; x + mlp(norm2(x))   (unified_transformer.py:64-90)."""
 
@@ -37,7 +42,7 @@ class UnifiedTransformerBlock(nn.Module):
     # ---- fused path (csrc/erv_block_fused.cu): two kernels around the attention core instead of ~14 library ops
     def _fused(self, x: torch.Tensor) -> bool:
         att = self.attention
-        if not (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled()):
+        if not (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and _autocast_ok()):
             return False
         if not (hasattr(att, "core") and hasattr(att, "qkv") and hasattr(att, "proj") and hasattr(att, "proj_dropout")):
             return False
@@ -49,6 +54,10 @@ class UnifiedTransformerBlock(nn.Module):
         att = self.attention
         att.before_qkv(x.shape, self.rpe)
         qkv = ops.block_ln_qkv(x, self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, self.norm1.eps)
+        if torch.is_autocast_enabled():
+            # bf16 autocast: the attention core sees the bf16 qkv an autocast Linear would hand it; LayerNorm, the
+            # projections and the MLP stay in fp32 (more accurate than the reference's autocast run, same interface)
+            qkv = qkv.to(torch.bfloat16)
         a = att.core(qkv, x.shape, self.rpe)
         p = self.mlp[2].p if self.training else 0.0
         seed = ops.dropout_seed(x.device) if p > 0 else None
@@ -111,7 +120,7 @@ class BaseViT(nn.Module):
 
     def _fused_ends(self, x: torch.Tensor) -> bool:
         """The embedding / head+loss kernels of csrc/erv_embed_head.cu apply (fp32 CUDA, dim 32, no autocast)."""
-        return (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled()
+        return (ops.FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and _autocast_ok()
                 and self.patch_embedding.weight.dtype == torch.float32 and self.patch_embedding.bias is not None
                 and ops.embed_supported(self.dim, self.patch_dim))
 

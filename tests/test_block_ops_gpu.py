@@ -223,3 +223,25 @@ def test_fused_embed_and_head_loss_match_library_path(cfg, patch, bsz, monkeypat
     monkeypatch.setattr(ops, "FUSED_BLOCK", True)
     logits = model(img)  # the plain forward keeps its meaning
     assert abs(float(torch.nn.functional.cross_entropy(logits, lab)) - float(res[0][0])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["performer_favor_circulant", "baseline_rope", "performer_relu_most_general"])
+def test_fused_path_under_bf16_autocast(name, monkeypatch):
+    """Under bf16 autocast the fused block / embedding / head kernels stay in fp32 and hand the attention core bf16 qkv:
+    loss and gradients agree with the op-by-op autocast path within the bf16 budget (2e-2), and are closer to fp32."""
+    from erv_b200 import CIFAR10_CONFIG, create_model, ops
+    torch.manual_seed(6)
+    model = create_model(name, CIFAR10_CONFIG, patch_size=4, dropout=0.0).to("cuda").eval()
+    img, lab = torch.randn(8, 3, 32, 32, device="cuda"), torch.randint(0, 10, (8,), device="cuda")
+    res = {}
+    for key, fused, ac in (("fused_bf16", True, True), ("plain_bf16", False, True), ("fp32", True, False)):
+        monkeypatch.setattr(ops, "FUSED_BLOCK", fused)
+        model.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+            loss = model.loss(img, lab)
+        loss.backward()
+        res[key] = (float(loss), {k: p.grad.float().clone() for k, p in model.named_parameters()})
+    assert abs(res["fused_bf16"][0] - res["fp32"][0]) < 2e-2 and abs(res["plain_bf16"][0] - res["fp32"][0]) < 5e-2
+    worst_f = max(rel_l2(res["fused_bf16"][1][k], res["fp32"][1][k]) for k in res["fp32"][1])
+    worst_p = max(rel_l2(res["plain_bf16"][1][k], res["fp32"][1][k]) for k in res["fp32"][1])
+    assert worst_f < 4e-2 and worst_f <= worst_p * 1.5, (worst_f, worst_p)
