@@ -73,8 +73,11 @@ class Trainer:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream: allocator, cuBLAS handles, lazy kernel loads
+            keep = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)]
             for _ in range(3):
                 self._step_impl(*self._static)
+            for dst, src in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), keep):
+                dst.copy_(src)  # the warm-up steps must not train: the first replay is optimisation step 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
@@ -139,6 +142,78 @@ class Trainer:
         self._stage_free[slot].record(cur)
         return loss
 
+    # ---- optimizer state in torch.optim.Adam's layout (checkpoint interchange) -----------------
+    def state_dict(self) -> dict:
+        """The optimizer half of a reference checkpoint: what torch.optim.Adam(model.parameters()).state_dict() holds after
+        the same steps (experiments/utils/training.py:393-398), so either side can resume the other's run."""
+        steps = int(self.step_count)
+        state = {}
+        if steps > 0:
+            for i, (p, n, off) in enumerate(zip(self.params, self.fp.sizes, self.fp.offsets)):
+                state[i] = {"step": torch.tensor(float(steps)),
+                            "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": self.decoupled, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict):
+        """Accepts torch.optim.Adam / AdamW state (one parameter group, no amsgrad).  Copies in place, so a captured graph
+        keeps working."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("expected one parameter group covering every trainable parameter, in model.parameters() order")
+        g = groups[0]
+        if g.get("amsgrad", False) or g.get("maximize", False):
+            raise ValueError("amsgrad / maximize are not supported by the fused flat Adam step")
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.weight_decay = float(g.get("weight_decay", 0.0))
+        self.decoupled = bool(g.get("decoupled_weight_decay", self.decoupled))
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (p, n, off) in enumerate(zip(self.params, self.fp.sizes, self.fp.offsets)):
+            st = sd["state"].get(g["params"][i])
+            if st is None:
+                steps.add(0)
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i} has shape {tuple(st['exp_avg'].shape)}, parameter {tuple(p.shape)}")
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise ValueError(f"parameters are at different step counts {sorted(steps)}; the flat step keeps one counter")
+        self.step_count.fill_(steps.pop())
+        if self._graph is not None:  # hyper-parameters are baked into a recorded step
+            self._graph = None
+
     def kernels_per_step(self) -> Optional[int]:
         """erv kernels launched per step in graph mode (counted while the graph was recorded)."""
         return getattr(self, "graph_kernels", None)
+
+
+def save_checkpoint(model: torch.nn.Module, optimizer, epoch: int, metrics: dict, filepath: str,
+                    model_name: Optional[str] = None):
+    """Same file layout as the reference's save_checkpoint (experiments/utils/training.py:373-412): `optimizer` is a
+    Trainer or a torch optimizer; the file loads on either side."""
+    ckpt = {"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
+            "metrics": metrics}
+    name = getattr(model, "model_name", None) or model_name
+    if name:
+        ckpt["model_name"] = name
+    for key in ("attention_type", "rpe_type"):
+        if hasattr(model, key):
+            ckpt[key] = getattr(model, key)
+    torch.save(ckpt, filepath)
+
+
+def load_checkpoint(model: torch.nn.Module, optimizer, filepath: str):
+    """Reference load_checkpoint (experiments/utils/training.py:415-443): returns (epoch, metrics).  Parameters are copied
+    in place, so a Trainer's flat buffers (and a captured graph) stay valid.  Pass the Trainer as `optimizer`."""
+    ckpt = torch.load(filepath, map_location=next(model.parameters()).device)
+    model.load_state_dict(ckpt["model_state_dict"])
+    if optimizer is not None:
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    return ckpt.get("epoch", 0), ckpt.get("metrics", {})
