@@ -68,41 +68,70 @@ __device__ __forceinline__ void load_rows(float* __restrict__ dst, const float* 
   }
 }
 
-// 4x4 micro-tile of scores: rows ty+16r, cols tx+16c
+// Number of micro-tile rows (or columns) base, base+16, base+32, base+48 that fall inside the sequence.
+__device__ __forceinline__ int valid_count(int base, int N) {
+  const int rem = N - base;
+  return rem <= 0 ? 0 : min(4, (rem + 15) >> 4);
+}
+
+// 4x4 micro-tile of scores: rows ty+16r, cols tx+16c.  nr / nc = valid_count of the thread's rows / columns: sequences of
+// 64k+1 tokens end in a tile with one live row (or column), where most threads have nothing to compute and the rest a
+// sliver; entries outside the sequence come back as 0.
 __device__ __forceinline__ void tile_scores(float (&s)[4][4], const float* __restrict__ Qs, const float* __restrict__ Ks,
-                                            int KD, int ty, int tx) {
+                                            int KD, int ty, int tx, int nr, int nc) {
   const int LDQ = KD + 4;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) s[r][c] = 0.f;
+  if (nr == 0 || nc == 0) return;
+  if (nr == 4 && nc == 4) {
+    for (int k = 0; k < KD; k += 4) {
+      float4 q[4], kk[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) q[r] = ld4(Qs + (ty + 16 * r) * LDQ + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kk[c] = ld4(Ks + (tx + 16 * c) * LDQ + k);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s[r][c] = fmaf(q[r].x, kk[c].x, s[r][c]);
+          s[r][c] = fmaf(q[r].y, kk[c].y, s[r][c]);
+          s[r][c] = fmaf(q[r].z, kk[c].z, s[r][c]);
+          s[r][c] = fmaf(q[r].w, kk[c].w, s[r][c]);
+        }
+    }
+    return;
+  }
   for (int k = 0; k < KD; k += 4) {
-    float4 q[4], kk[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) q[r] = ld4(Qs + (ty + 16 * r) * LDQ + k);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) kk[c] = ld4(Ks + (tx + 16 * c) * LDQ + k);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r) {
+      if (r >= nr) break;
+      const float4 q = ld4(Qs + (ty + 16 * r) * LDQ + k);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        s[r][c] = fmaf(q[r].x, kk[c].x, s[r][c]);
-        s[r][c] = fmaf(q[r].y, kk[c].y, s[r][c]);
-        s[r][c] = fmaf(q[r].z, kk[c].z, s[r][c]);
-        s[r][c] = fmaf(q[r].w, kk[c].w, s[r][c]);
+        if (c >= nc) break;
+        const float4 kk = ld4(Ks + (tx + 16 * c) * LDQ + k);
+        s[r][c] = fmaf(q.x, kk.x, s[r][c]);
+        s[r][c] = fmaf(q.y, kk.y, s[r][c]);
+        s[r][c] = fmaf(q.z, kk.z, s[r][c]);
+        s[r][c] = fmaf(q.w, kk.w, s[r][c]);
       }
+    }
   }
 }
 
 // 4x4 micro-tile of X Y^T for two token tiles [64][DH+4] (dP = dO V^T)
 template <int DH>
 __device__ __forceinline__ void tile_outer(float (&s)[4][4], const float* __restrict__ X, const float* __restrict__ Y,
-                                           int ty, int tx) {
+                                           int ty, int tx, int nr, int nc) {
   constexpr int LDM = DH + 4;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) s[r][c] = 0.f;
+  if (nr == 0 || nc == 0) return;
 #pragma unroll
   for (int k = 0; k < DH; k += 4) {
     float4 q[4], kk[4];
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(256) tile_fwd_kernel(const TileArgs p) {
     }
     __syncthreads();
     float s[4][4];
-    tile_scores(s, Qs, Ks, p.KD, ty, tx);
+    tile_scores(s, Qs, Ks, p.KD, ty, tx, valid_count(i0 + ty, N), valid_count(j0 + tx, N));
     if (MODE == MODE_KERPLE) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -248,7 +277,8 @@ __global__ void __launch_bounds__(256) tile_fwd_kernel(const TileArgs p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[u][e] *= alpha;
       const float* prowp = Ps + prow * LDP;
-      for (int j = 0; j < TQ; j += 4) {
+      const int jend = (i0 + prow < N) ? min(TQ, (N - j0 + 3) & ~3) : 0;  // keys past the sequence carry zero weight
+      for (int j = 0; j < jend; j += 4) {
         const float4 pv = ld4(prowp + j);
         const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
@@ -288,7 +318,7 @@ __global__ void __launch_bounds__(256) tile_fwd_kernel(const TileArgs p) {
       load_rows(Ks, krows, p.ldr, p.KD, j0, N);
       __syncthreads();
       float s[4][4];
-      tile_scores(s, Qs, Ks, p.KD, ty, tx);
+      tile_scores(s, Qs, Ks, p.KD, ty, tx, valid_count(i0 + ty, N), valid_count(j0 + tx, N));
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int il = ty + 16 * r, i = i0 + il;
@@ -421,12 +451,14 @@ __global__ void __launch_bounds__(256) tile_bwd_dq_kernel(const TileArgs p) {
     }
     __syncthreads();
     float s[4][4], dp[4][4];
-    tile_scores(s, Qs, Ks, KD, ty, tx);
-    tile_outer<DH>(dp, dOs, Vs, ty, tx);
+    const int nr = valid_count(i0 + ty, N), nc = valid_count(j0 + tx, N);
+    tile_scores(s, Qs, Ks, KD, ty, tx, nr, nc);
+    tile_outer<DH>(dp, dOs, Vs, ty, tx, nr, nc);
     bwd_tile_weights<MODE>(p, s, dp, Ps, Gs, cs, rowA, rowB, pair, b, i0, j0, ty, tx, keep_scale, true);
     __syncthreads();
     // dQ[i][k] += sum_j G[i][j] K[j][k]; thread: rows ty+16r, cols tx+16c+64ch
-    for (int j = 0; j < TQ; j += 4) {
+    const int jend = (nr > 0) ? min(TQ, (N - j0 + 3) & ~3) : 0;  // G is zero outside the sequence
+    for (int j = 0; j < jend; j += 4) {
       float4 g[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) g[r] = ld4(Gs + (ty + 16 * r) * LDP + j);
@@ -527,12 +559,15 @@ __global__ void __launch_bounds__(256) tile_bwd_dkv_kernel(const TileArgs p) {
     bwd_row_stats<T, DH, MODE>(p, rowA, rowB, dOs, pair, b, h, i0);
     __syncthreads();
     float s[4][4], dp[4][4];
-    tile_scores(s, Qs, Ks, KD, ty, tx);          // s[r][c]: query ty+16r, key tx+16c
-    tile_outer<DH>(dp, dOs, Vs, ty, tx);
+    const int nr = valid_count(i0 + ty, N), nc = valid_count(j0 + tx, N);
+    tile_scores(s, Qs, Ks, KD, ty, tx, nr, nc);  // s[r][c]: query ty+16r, key tx+16c
+    tile_outer<DH>(dp, dOs, Vs, ty, tx, nr, nc);
     bwd_tile_weights<MODE>(p, s, dp, Ps, Gs, cs, rowA, rowB, pair, b, i0, j0, ty, tx, keep_scale, true);
     __syncthreads();
     // dK[j][k] += sum_i G[i][j] Q[i][k]; rows j = ty+16r
-    for (int i = 0; i < TQ; ++i) {
+    const int iend_all = min(TQ, N - i0);  // queries past the sequence contribute nothing
+    const int iend = (valid_count(j0 + ty, N) > 0) ? iend_all : 0;
+    for (int i = 0; i < iend; ++i) {
       float g[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) g[r] = Gs[i * LDP + ty + 16 * r];
@@ -548,7 +583,8 @@ __global__ void __launch_bounds__(256) tile_bwd_dkv_kernel(const TileArgs p) {
         }
     }
     // dV[j][d] += sum_i W[i][j] * (dO[i][d] * (kerple ? r_i : 1))
-    for (int i = 0; i < TQ; ++i) {
+    const int iend_v = (j0 + prow < N) ? iend_all : 0;
+    for (int i = 0; i < iend_v; ++i) {
       float w = Ps[i * LDP + prow];
       if (MODE == MODE_KERPLE) w *= rowA[i];
 #pragma unroll
@@ -594,15 +630,28 @@ __global__ void exp_kernel(const float* __restrict__ x, float* __restrict__ y, s
 }
 
 // dbias[h][d] = sum over (b, qtile) of part[(b*H+h)*nqt + t][d]
-__global__ void dbias_reduce_kernel(const float* __restrict__ part, float* __restrict__ dbias, int B, int H, int nqt,
-                                    int W) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)H * W) return;
-  int h = (int)(i / W), d = (int)(i % W);
+// d bias[h][d] = sum over (batch, query tile) of the per-CTA partials.  Block (32, 32): x = diagonal (coalesced), y = slice of
+// the B*nqt partials; the 32 slice sums are then added in a fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(1024) dbias_reduce_kernel(const float* __restrict__ part, float* __restrict__ dbias,
+                                                            int B, int H, int nqt, int W) {
+  __shared__ float red[32][33];
+  const size_t i = (size_t)blockIdx.x * 32 + threadIdx.x;
+  const bool live = i < (size_t)H * W;
+  const int h = live ? (int)(i / W) : 0, d = live ? (int)(i % W) : 0;
   float acc = 0.f;
-  for (int b = 0; b < B; ++b)
-    for (int t = 0; t < nqt; ++t) acc += part[(((size_t)b * H + h) * nqt + t) * W + d];
-  dbias[i] = acc;
+  if (live)
+    for (int u = threadIdx.y; u < B * nqt; u += 32) {
+      const int b = u / nqt, t = u % nqt;
+      acc += part[(((size_t)b * H + h) * nqt + t) * W + d];
+    }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    float sum = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) sum += red[y][threadIdx.x];
+    dbias[i] = sum;
+  }
 }
 
 // q and k of the packed buffer -> rotated fp32 rows [2][B*H][N][DH]   (softmax prologue)
@@ -912,7 +961,7 @@ extern "C" int erv_kerple_attention_bwd(const void* qkv, const void* out, const 
   if (rc) return rc;
   {
     size_t nb = (size_t)H * (2 * N - 1);
-    dbias_reduce_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((const float*)(ws + w.dpart), dbias, B, H, nqt,
+    dbias_reduce_kernel<<<(unsigned)((nb + 31) / 32), dim3(32, 32), 0, st>>>((const float*)(ws + w.dpart), dbias, B, H, nqt,
                                                                       2 * N - 1);
     ERV_LAUNCH_CHECK();
   }
