@@ -727,9 +727,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       };
       // G (in pr) x [W^T | 1]: this thread's partial sums
       auto gradient_partial = [&](float (&acc)[RW]) {
-        unsigned long long a2[RW / 2];  // packed pairs: FFMA2 halves the issue slots of this FMA-bound loop
+        // packed pairs: FFMA2 halves the issue slots of the loop; what bounds it is the shared-memory reads of the W^T rows,
+        // so the ones column (row sum of G; padded features carry G = 0) is a plain add instead of a fifth 128-bit load
+        unsigned long long a2[DH / 2];
+        float ones_a = 0.f, ones_b = 0.f;
 #pragma unroll
-        for (int j = 0; j < RW / 2; ++j) a2[j] = 0ull;
+        for (int j = 0; j < DH / 2; ++j) a2[j] = 0ull;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int f0 = feat0(c);
@@ -738,18 +741,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             const float gq = __uint_as_float(pr[c][i]);
             const float* wr = w32 + (f0 + i) * RW;
 #pragma unroll
-            for (int cd = 0; cd < RW / 4; ++cd) {
+            for (int cd = 0; cd < DH / 4; ++cd) {
               const float4 a = ld4(wr + 4 * cd);
               ffma2(a2[2 * cd], gq, a.x, a.y);
               ffma2(a2[2 * cd + 1], gq, a.z, a.w);
             }
+            if (i & 1) ones_b += gq; else ones_a += gq;
           }
         }
 #pragma unroll
-        for (int j = 0; j < RW / 2; ++j) {
+        for (int j = 0; j < DH / 2; ++j) {
           acc[2 * j] = lo_of(a2[j]);
           acc[2 * j + 1] = hi_of(a2[j]);
         }
+        acc[DH] = ones_a + ones_b;
+#pragma unroll
+        for (int j = DH + 1; j < RW; ++j) acc[j] = 0.f;
       };
       // reduced sums (part 0) -> gradient wrt the raw q/k row, written to global memory
       auto store_input_gradient = [&](const float (&acc)[RW]) {

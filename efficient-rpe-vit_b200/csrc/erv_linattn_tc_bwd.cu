@@ -351,13 +351,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
                   const float g = __uint_as_float(pr[c][i]);
                   const float* wr = w32 + (f0 + i) * RW;
 #pragma unroll
-                  for (int cd = 0; cd < RW / 4; ++cd) {
+                  for (int cd = 0; cd < DH / 4; ++cd) {
                     const float4 a = ld4(wr + 4 * cd);
                     acc[4 * cd] = fmaf(g, a.x, acc[4 * cd]);
                     acc[4 * cd + 1] = fmaf(g, a.y, acc[4 * cd + 1]);
                     acc[4 * cd + 2] = fmaf(g, a.z, acc[4 * cd + 2]);
                     acc[4 * cd + 3] = fmaf(g, a.w, acc[4 * cd + 3]);
                   }
+                  acc[DH] += g;  // ones column of [W^T|1] (padded features carry G = 0): no fifth shared-memory load
                 }
               }
           }
