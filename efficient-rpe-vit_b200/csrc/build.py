@@ -17,6 +17,8 @@ LIB = os.path.join(OUT_DIR, "liberv_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
          "-Xcompiler", "-fPIC"]
+if os.environ.get("ERV_TRACE"):  # phase trace points of the backward kernels (tools/trace_bwd.py); rebuild with force=True
+    FLAGS.append("-DERV_TRACE")
 
 
 def _newer(target, deps):

@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t ph_a = 0, ph_b = 0, ph_c = 0;
   int tr_i = 0;
+  // phase trace (tools/trace_bwd.py): compiled in only with -DERV_TRACE, so the production kernel carries no checks
+#ifdef ERV_TRACE
   auto TR = [&](int tag) {
     if (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && tr_i < 1000) {
       p.trace[2 * tr_i] = tag;
@@ -206,6 +208,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       ++tr_i;
     }
   };
+#else
+  auto TR = [](int) {};
+  (void)tr_i;
+#endif
 
   const T* qkv = static_cast<const T*>(p.qkv);
   const T* outp = static_cast<const T*>(p.out);

@@ -11,4 +11,5 @@ for spec in "la_tc2_fwd_kernel fwd" "la_tc2_bwd_kernel bwd" "mlp_bwd_tc_kernel m
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_ll_$TAG.log 2>&1
 bash tools/bench_configs.sh
+ncu --set full --clock-control none --import-source on -k regex:tile_bwd_dkv_kernel -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_kerple_dkv python bench.py --workload config3 --batch 1024 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${TAG}_kerple.log 2>&1
 ls -la gpurun_out | grep $TAG

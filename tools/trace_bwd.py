@@ -1,3 +1,4 @@
+# needs a library built with the trace points: ERV_TRACE=1 python -c "import sys; sys.path.insert(0, 'efficient-rpe-vit_b200/csrc'); import build; build.build(force=True)"
 import sys, torch, collections
 sys.path.insert(0,'efficient-rpe-vit_b200')
 from erv_b200 import ops, _capi as C
