@@ -44,10 +44,13 @@ __device__ __forceinline__ void load_row(const T* __restrict__ p, float (&x)[DH]
   }
 }
 
-// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
+// RoPE / Circulant-STRING rotation of one token row.  Deliberately out of line: the rotations are 0.3-0.6 k instructions per call
+// site, the short-sequence kernels inline their caller at three to four sites, and those kernels are instruction-fetch bound
+// (profiles/r01_final_ncu_attention.md: no_inst is their top stall reason), so the un-rotated path should not have to jump over
+// that code.  The row goes through local memory only on the rotated path.
 template <int DH>
-__device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const float* __restrict__ ta,
-                                             const float* __restrict__ tb, int h, int n, int N, float prescale) {
+__device__ __noinline__ void rotate_row(float* __restrict__ x, int rot, const float* __restrict__ ta,
+                                        const float* __restrict__ tb, int h, int n, int N) {
   if (rot == ERV_ROT_ROPE) {
 #pragma unroll
     for (int m = 0; m < DH / 2; ++m) {
@@ -57,17 +60,31 @@ __device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const floa
       x[2 * m + 1] = xe * s + xo * c;
     }
   } else if (rot == ERV_ROT_CIRCULANT) {
-    float g[DH], y[DH];
+    float g[DH], xin[DH];
     load_row<float, DH>(ta + ((size_t)h * N + n) * DH, g);
+#pragma unroll
+    for (int a = 0; a < DH; ++a) xin[a] = x[a];
 #pragma unroll
     for (int a = 0; a < DH; ++a) {
       float acc = 0.f;
 #pragma unroll
-      for (int b = 0; b < DH; ++b) acc = fmaf(g[(a - b) & (DH - 1)], x[b], acc);
-      y[a] = acc;
+      for (int b = 0; b < DH; ++b) acc = fmaf(g[(a - b) & (DH - 1)], xin[b], acc);
+      x[a] = acc;
     }
+  }
+}
+
+// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
+template <int DH>
+__device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const float* __restrict__ ta,
+                                             const float* __restrict__ tb, int h, int n, int N, float prescale) {
+  if (rot != ERV_ROT_NONE) {
+    float t[DH];
 #pragma unroll
-    for (int a = 0; a < DH; ++a) x[a] = y[a];
+    for (int a = 0; a < DH; ++a) t[a] = x[a];
+    rotate_row<DH>(t, rot, ta, tb, h, n, N);
+#pragma unroll
+    for (int a = 0; a < DH; ++a) x[a] = t[a];
   }
 #pragma unroll
   for (int a = 0; a < DH; ++a) x[a] *= prescale;
