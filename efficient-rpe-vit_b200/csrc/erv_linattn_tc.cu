@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
           float n2 = INFINITY;  // invalid rows: exponent -inf -> phi = 0
           if (valid) {
             load_row<T, DH>((pass == 0 ? kb : qb) + (size_t)n * tok_stride, x);
-            prologue_row<DH>(x, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+            prologue_row<DH, true>(x, p.rot, p.ta, p.tb, h, n, N, p.prescale);
             n2 = 0.f;
 #pragma unroll
             for (int a = 0; a < DH; ++a) n2 = fmaf(x[a], x[a], n2);

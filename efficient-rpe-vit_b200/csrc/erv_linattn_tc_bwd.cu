@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           float n2 = INFINITY;
           if (valid) {
             load_row<T, DH>(xb + (size_t)n * tok_stride, rowv);
-            prologue_row<DH>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
+            prologue_row<DH, true>(rowv, p.rot, p.ta, p.tb, h, n, N, p.prescale);
             n2 = 0.f;
 #pragma unroll
             for (int a = 0; a < DH; ++a) n2 = fmaf(rowv[a], rowv[a], n2);

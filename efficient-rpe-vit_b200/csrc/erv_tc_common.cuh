@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_row(const T* __restrict__ p, float (&x)[DH]
 // (profiles/r01_final_ncu_attention.md: no_inst is their top stall reason), so the un-rotated path should not have to jump over
 // that code.  The row goes through local memory only on the rotated path.
 template <int DH>
-__device__ __noinline__ void rotate_row(float* __restrict__ x, int rot, const float* __restrict__ ta,
+__device__ __forceinline__ void rotate_row_impl(float* __restrict__ x, int rot, const float* __restrict__ ta,
                                         const float* __restrict__ tb, int h, int n, int N) {
   if (rot == ERV_ROT_ROPE) {
 #pragma unroll
@@ -74,11 +74,20 @@ __device__ __noinline__ void rotate_row(float* __restrict__ x, int rot, const fl
   }
 }
 
-// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
 template <int DH>
+__device__ __noinline__ void rotate_row(float* __restrict__ x, int rot, const float* __restrict__ ta,
+                                        const float* __restrict__ tb, int h, int n, int N) {
+  rotate_row_impl<DH>(x, rot, ta, tb, h, n, N);
+}
+
+// rotation (RoPE / Circulant-STRING) + Dh^-1/4 scale of one token row held in registers
+// INLINE_ROT: the long-sequence kernels (one call site, rotation on their hot path at BASELINE config 4) keep it inline.
+template <int DH, bool INLINE_ROT = false>
 __device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const float* __restrict__ ta,
                                              const float* __restrict__ tb, int h, int n, int N, float prescale) {
-  if (rot != ERV_ROT_NONE) {
+  if (INLINE_ROT) {
+    rotate_row_impl<DH>(x, rot, ta, tb, h, n, N);
+  } else if (rot != ERV_ROT_NONE) {
     float t[DH];
 #pragma unroll
     for (int a = 0; a < DH; ++a) t[a] = x[a];
