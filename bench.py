@@ -9,8 +9,14 @@ CrossEntropy.  Per-GPU batch is fixed (weak scaling).  Prints ONE JSON line on r
 
 Timed region: K steps between barrier+synchronize, CUDA events on the launching stream, max over ranks.  Inputs
 rotate through a device-resident pool larger than L2 (value) or through pinned host memory with the loss read back
-every step (e2e).  The roofline entry times the dominant attention kernel with CUDA events in a separate
-instrumented pass (same shapes, eager launches) so the instrumentation does not perturb `value`.
+every step (e2e; the K steps are repeated until the loop has run >= 0.5 s so the host-timed figure is stable).  The
+roofline entry times the dominant attention kernel with CUDA events in a separate instrumented pass (same shapes,
+eager launches) so the instrumentation does not perturb `value`.  `other_configs` times the other BASELINE configs
+(1, 3, 4, 4b, 5) in the same run with fewer steps; the headline stays config 2.
+
+The reference arm and the `cpu_baseline` leg run the UNMODIFIED reference (baseline/_ref, installed by
+tools/install_reference.py: create_model + torch.optim.Adam + CrossEntropy, experiments/utils/training.py:53-69,304-309)
+on the host cores at the GPU arm's batch; the oracle port is used only when baseline/_ref is absent (`kind` says which).
 """
 import argparse
 import json
@@ -40,6 +46,8 @@ WORKLOADS = {
                     desc="baseline softmax ViT, MNIST-shape synthetic 28x28x1, patch 7 (N=17), dim 32 heads 2 depth 3"),
     "config3": dict(model="performer_relu_most_general", image=32, channels=3, patch=4, num_features=None, autocast=None,
                     desc="performer_relu_most_general (KERPLE), CIFAR-10 shape, patch 4 (N=65), M=44"),
+    "config3_p8": dict(model="performer_relu_most_general", image=32, channels=3, patch=8, num_features=None, autocast=None,
+                       desc="performer_relu_most_general (KERPLE), CIFAR-10 shape, default patch 8 (N=17), M=44"),
     "config4": dict(model="performer_favor_circulant", image=224, channels=3, patch=16, num_features=None,
                     autocast="bf16", desc="performer_favor_circulant, 224x224x3 patch 16 (N=197), bf16 autocast"),
     "config4b": dict(model="baseline_rope", image=224, channels=3, patch=16, num_features=None, autocast="bf16",
@@ -120,12 +128,57 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+class _ReferenceTrainer:
+    """The reference itself (baseline/_ref): create_model + Adam(lr=1e-3) + CrossEntropy, train mode, on CPU.  Runs in THIS
+    process with baseline/_ref first on sys.path; only the reference arm / cpu_baseline leg construct it."""
+
+    def __init__(self, w, seed=0):
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "configs" or k.startswith("configs.")]:
+            del sys.modules[k]
+        sys.path.insert(0, REF_DIR)
+        try:
+            import importlib
+            models = importlib.import_module("models")
+            cfgs = importlib.import_module("configs")
+            assert os.path.realpath(models.__file__).startswith(os.path.realpath(REF_DIR)), models.__file__
+            import copy
+            base = copy.deepcopy(cfgs.CIFAR10_CONFIG)
+            base.update(image_size=w["image"], in_channels=w["channels"])
+            torch.manual_seed(seed)
+            acfg = {"num_features": w["num_features"]} if w["num_features"] else None
+            self.model = models.create_model(w["model"], base, attention_config=acfg, patch_size=w["patch"]).train()
+        finally:
+            sys.path.remove(REF_DIR)
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "configs" or k.startswith("configs.")]:
+                del sys.modules[k]  # the GPU arm must not see the reference's packages
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
+        self.autocast = w["autocast"] == "bf16"
+
+    def step(self, images, labels):
+        if self.autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                loss = torch.nn.functional.cross_entropy(self.model(images).float(), labels)
+        else:
+            loss = torch.nn.functional.cross_entropy(self.model(images), labels)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return float(loss.item())  # the reference's loop reads the loss every step (training.py:66-69)
+
+
 def cpu_reference_steps(w, batch, steps, warmup, budget_s=None):
-    """The reference's CPU path (oracle port, all host threads): images/s over `steps` steps of `batch` images."""
-    from oracle import erv_oracle as O
+    """The reference's CPU path, all host threads: images/s over `steps` steps of `batch` images.
+    Returns (images/s, ms/step, steps done, threads, kind)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = model_cfg(w)
-    tr = O.CpuTrainer(w["model"], cfg, seed=0)
+    kind = "reference" if os.path.isdir(os.path.join(REF_DIR, "models")) else "port"
+    if kind == "reference":
+        tr = _ReferenceTrainer(w)
+    else:
+        from oracle import erv_oracle as O
+        tr = O.CpuTrainer(w["model"], model_cfg(w), seed=0)
     g = torch.Generator().manual_seed(0)
     img = torch.randn(batch, w["channels"], w["image"], w["image"], generator=g)
     lab = torch.randint(0, 10, (batch,), generator=g)
@@ -139,72 +192,83 @@ def cpu_reference_steps(w, batch, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done * batch / dt, dt / done * 1e3, done, torch.get_num_threads()
+    return done * batch / dt, dt / done * 1e3, done, torch.get_num_threads(), kind
+
+
+def _kind_text(kind):
+    return ("the UNMODIFIED reference (baseline/_ref: create_model + torch.optim.Adam + CrossEntropy, eager CPU)"
+            if kind == "reference" else "oracle port of the reference's eager CPU path (baseline/_ref absent)")
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.cpu_batch
-    ips, ms, done, cores = cpu_reference_steps(w, batch, args.steps, min(args.warmup, 2))
+    batch = args.cpu_batch if args.cpu_batch else args.batch  # same batch per step as the GPU arm unless overridden
+    warm = min(args.warmup, 2)
+    ips, ms, done, cores, kind = cpu_reference_steps(w, batch, args.steps, warm, budget_s=args.cpu_budget)
+    small = None
+    if batch != 128 and args.workload == "config2":  # second figure: the reference config's own small batch favours the CPU
+        ips2, ms2, done2, _, _ = cpu_reference_steps(w, 128, 1000, 1, budget_s=8.0)
+        small = {"batch_per_step": 128, "value": ips2, "ms_per_step": ms2, "steps": done2}
     line = {
         "impl": "reference", "metric": "train images/sec (fwd+bwd)", "value": ips, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "batch_per_step": batch},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{done} training steps (fwd+bwd+Adam) of {batch} images, oracle port of the "
-                                   "reference's eager CPU path, all host threads"},
+        "n_gpus": args.gpus, "steps": done, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if w["autocast"] == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "batch_per_step": batch, "per_gpu_batch": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{done} training steps (fwd+bwd+Adam) of {batch} images, {_kind_text(kind)}, all host "
+                                   f"threads; stopped after {args.cpu_budget:.0f} s if not finished",
+                         "batch_128": small},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="erv", choices=["erv", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=128, help="images per CPU-baseline step")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return run_reference(args, w)
-    args.warmup = max(args.warmup, 3)
+def _peaks():
+    hbm, tens, src = 6650.0, 1590.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        hbm, tens, src = float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured"
+    except Exception:
+        pass
+    return hbm, tens, src
 
+
+def attention_flops(key, w, B, n_tok, M):
+    """Algorithmic FLOPs of one attention call, H = 2, Dh = 16."""
+    H, Dh = 2, 16
+    bwd = key.endswith("_bwd")
+    if key.startswith("linear"):
+        return (16 if bwd else 8) * B * H * n_tok * Dh * M
+    if key.startswith("softmax"):
+        return (10 if bwd else 4) * B * H * n_tok * n_tok * Dh
+    fwd = 2 * B * H * n_tok * n_tok * (M + Dh) + 4 * B * H * n_tok * Dh * M
+    # backward of the tile route: P recomputed, dA = dnum V^T (+ dden), dV = A^T dnum, dphi_q, dphi_k, feature maps twice
+    return 2 * B * H * n_tok * n_tok * (3 * M + 2 * Dh) + 8 * B * H * n_tok * Dh * M if bwd else fwd
+
+
+def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
+    """Times `steps` training steps of one workload on this rank's GPU (all ranks call it together).  Returns a dict."""
     import torch.distributed as dist
     from erv_b200 import CIFAR10_CONFIG, _capi, create_model, ops
     from erv_b200.train import Trainer
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    w = WORKLOADS[wname]
+    world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
 
     torch.manual_seed(0)  # same construction seed on every rank
     base = dict(CIFAR10_CONFIG, image_size=w["image"], in_channels=w["channels"])
     acfg = {"num_features": w["num_features"]} if w["num_features"] else None
     model = create_model(w["model"], base, attention_config=acfg, patch_size=w["patch"]).to(dev).train()
     autocast = torch.bfloat16 if w["autocast"] == "bf16" else None
-    trainer = Trainer(model, lr=1e-3, use_graph=not args.no_graph, autocast_dtype=autocast)
+    trainer = Trainer(model, lr=1e-3, use_graph=use_graph, autocast_dtype=autocast)
 
-    B = args.batch
     img_bytes = B * w["channels"] * w["image"] * w["image"] * 4
     pool_n = max(2, min(64, L2_BYTES // img_bytes + 2))  # device pool > L2 so inputs are never L2-resident
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     pool = [(torch.randn(B, w["channels"], w["image"], w["image"], device=dev, generator=g),
              torch.randint(0, 10, (B,), device=dev, generator=g)) for _ in range(pool_n)]
-    host_pool = [(i.cpu().pin_memory(), l.cpu().pin_memory()) for i, l in pool[:min(pool_n, 8)]]
 
     def barrier():
         if world > 1:
@@ -218,7 +282,7 @@ def main():
         return float(t.item())
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         trainer.step(*pool[i % pool_n])
     barrier()
     sampler = ClockSampler(local)
@@ -226,7 +290,7 @@ def main():
     _capi.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         loss = trainer.step(*pool[i % pool_n])
     e1.record()
     barrier()
@@ -234,94 +298,164 @@ def main():
     clocks = sampler.stop()
     eager_launches = _capi.launch_count()
     per_step = trainer.kernels_per_step()
-    gpu_launches = per_step * args.steps if per_step is not None else eager_launches
-    final_loss = float(loss.item())
-    ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
+    res = {"ms_per_step": ms_total / steps, "value": world * B * steps / (ms_total / 1e3), "clocks": clocks,
+           "gpu_launches": per_step * steps if per_step is not None else eager_launches,
+           "final_loss": float(loss.item()), "pool_n": pool_n, "img_bytes": img_bytes,
+           "dtype": "bf16" if autocast is not None else "f32", "tokens": (w["image"] // w["patch"]) ** 2 + 1}
 
     # ---- e2e: host buffers in, loss out, every step ------------------------------------------------------
     # Every step's batch starts in pinned host memory and its loss is read back on the host; the copy of batch i+1 is
     # issued (side stream, double-buffered staging) before the host waits for the loss of batch i, as a data loader
-    # with pin_memory / non_blocking copies does.
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    for i in range(2):
-        trainer.step(*host_pool[i % len(host_pool)])
-    barrier()
-    t0 = time.perf_counter()
-    trainer.prefetch(*host_pool[0])
-    for i in range(args.steps):
-        l = trainer.step_prefetched()
-        if i + 1 < args.steps:
-            trainer.prefetch(*host_pool[(i + 1) % len(host_pool)])
-        loss_host.copy_(l, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": "images/s",
-           "h2d_bytes_per_step": world * (img_bytes + B * 8), "d2h_bytes_per_step": world * 4}
+    # with pin_memory / non_blocking copies does.  The K-step loop is repeated until it has run for >= 0.5 s.
+    if do_e2e:
+        host_pool = [(i.cpu().pin_memory(), l.cpu().pin_memory()) for i, l in pool[:min(pool_n, 8)]]
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            trainer.step(*host_pool[i % len(host_pool)])
+        reps = max(1, int(0.5 / max(1e-6, ms_total / 1e3)) + 1)
+        n_e2e = steps * reps
+        barrier()
+        t0 = time.perf_counter()
+        trainer.prefetch(*host_pool[0])
+        for i in range(n_e2e):
+            l = trainer.step_prefetched()
+            if i + 1 < n_e2e:
+                trainer.prefetch(*host_pool[(i + 1) % len(host_pool)])
+            loss_host.copy_(l, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        res["e2e"] = {"value": world * B * n_e2e / e2e_s, "unit": "images/s",
+                      "h2d_bytes_per_step": world * (img_bytes + B * 8), "d2h_bytes_per_step": world * 4,
+                      "steps_timed": n_e2e}
 
     # ---- roofline: dominant attention kernel, CUDA events around its launches (separate eager pass) --------
-    roofline = None
     ops.PROFILE = {}
     for i in range(6):  # every rank runs the pass (the step contains the gradient all-reduce)
         trainer._step_impl(*pool[i % pool_n])
     torch.cuda.synchronize()
     stats = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.PROFILE.items()}
     ops.PROFILE = None
+    res["roofline"] = None
     if rank == 0:
-        n_tok = (w["image"] // w["patch"]) ** 2 + 1
+        n_tok = res["tokens"]
         esize = 2 if autocast is not None else 4
         per_call = {k: statistics.mean(v[len(v) // 3:]) for k, v in stats.items() if v}  # drop the first third (warm-up)
         if per_call:
             dom = max(per_call, key=lambda k: per_call[k])
             factor = 8 if dom.endswith("_bwd") else 4  # fwd 4*B*N*C*s, bwd 8*B*N*C*s
             alg_bytes = factor * B * n_tok * 32 * esize
-            peak, src = 6650.0, "fallback"
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    peak, src = float(json.load(f)["hbm_gbs"]), "measured"
-            except Exception:
-                pass
-            achieved = alg_bytes / (per_call[dom] * 1e-3) / 1e9
-            traffic = None  # dram bytes per launch of this kernel at this workload, from the committed ncu capture
-            try:
+            M = w["num_features"] or 44
+            flops = attention_flops(dom, w, B, n_tok, M)
+            hbm, tens, src = _peaks()
+            t = per_call[dom] * 1e-3
+            gbs, tfs = alg_bytes / t / 1e9, flops / t / 1e12
+            # tensor-pipe-bound only for softmax / KERPLE tiles at N >= 4097; everything else HBM-bound
+            tensor_bound = n_tok >= 1024 and not dom.startswith("linear")
+            traffic, traffic_source = None, None
+            try:  # dram bytes per launch of this kernel from a COMMITTED ncu capture (not measured by this run)
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    traffic = json.load(f).get(f"{args.workload}:{B}", {}).get(dom)
+                    ent = json.load(f).get(f"{wname}:{B}", {})
+                traffic, traffic_source = ent.get(dom), ent.get("source")
             except Exception:
                 pass
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": traffic, "peak_source": src, "ms_per_launch": per_call[dom],
-                        "algorithmic_bytes": alg_bytes,
-                        "attention_ms_per_step": sum(per_call.values()) * 3,
-                        "per_call_ms": per_call}
+            res["roofline"] = {
+                "bound": "tensor" if tensor_bound else "hbm", "kernel": dom,
+                "achieved": tfs if tensor_bound else gbs, "peak": tens if tensor_bound else hbm,
+                "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": (tfs / tens) if tensor_bound else (gbs / hbm), "traffic": traffic,
+                "traffic_source": traffic_source, "peak_source": src, "ms_per_launch": per_call[dom],
+                "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops, "hbm_gbs": gbs, "tflops": tfs,
+                "attention_ms_per_step": sum(per_call.values()) * 3, "per_call_ms": per_call}
+    if world > 1:
+        barrier()
+    trainer._graph = None
+    del trainer, model, pool
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="erv", choices=["erv", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU step (0 = the GPU arm's per-GPU batch)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="reference arm: stop after this many seconds")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    env = {"world": world, "rank": rank, "local": local, "dev": dev}
+
+    B = args.batch
+    head = measure(args.workload, B, args.steps, args.warmup, env, do_e2e=True, use_graph=not args.no_graph)
+
+    # ---- the other BASELINE configs, same run, fewer steps (per-GPU batch in brackets) --------------------------
+    other = {}
+    if args.workload == "config2" and not args.no_other_configs:
+        plan = [("config1", 128), ("config3", 1024), ("config3_p8", 1024), ("config4", 256), ("config4b", 256), ("config5", 2)]
+        if world >= 8:
+            plan.append(("config5", 8))
+        k = max(3, min(args.steps, 20))
+        for name, b in plan:
+            try:
+                r = measure(name, b, k, 3, env, do_e2e=False)
+                rf = r["roofline"]
+                other[f"{name}:b{b}"] = {
+                    "workload": WORKLOADS[name]["desc"], "per_gpu_batch": b, "value": r["value"], "unit": "images/s",
+                    "ms_per_step": r["ms_per_step"], "steps": k, "dtype": r["dtype"], "tokens": r["tokens"],
+                    "roofline": None if rf is None else {kk: rf[kk] for kk in
+                                                         ("bound", "kernel", "achieved", "peak", "unit", "frac",
+                                                          "ms_per_launch", "hbm_gbs", "tflops", "per_call_ms")}}
+            except Exception as exc:  # a config that cannot run must not take the headline down with it
+                other[f"{name}:b{b}"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, done, cores = cpu_reference_steps(w, args.cpu_batch, 1000, 1, budget_s=15.0)
-        cpu_baseline = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"{done} training steps (fwd+bwd+Adam) of {args.cpu_batch} images (~15 s), oracle "
-                                  "port of the reference's eager CPU path, all host threads"}
+        cb = args.cpu_batch if args.cpu_batch else B
+        ips, ms, done, cores, kind = cpu_reference_steps(w, cb, 1000, 1, budget_s=20.0)
+        cpu_baseline = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "ms_per_step": ms,
+                        "sample": f"{done} training steps (fwd+bwd+Adam) of {cb} images (~20 s), {_kind_text(kind)}, "
+                                  "all host threads"}
 
     if rank == 0:
         line = {
-            "metric": "train images/sec (fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if autocast is not None else "f32",
-            "data": "synthetic",
-            "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "tokens": None,
+            "metric": "train images/sec (fwd+bwd)", "value": head["value"], "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "tokens": head["tokens"],
                        "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-3 (fused, flat)", "cuda_graph": not args.no_graph,
-                       "l2_policy": f"inputs rotate through a {pool_n}-batch device pool ({pool_n * img_bytes >> 20} MiB > L2)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "final_loss": final_loss,
+                       "l2_policy": f"inputs rotate through a {head['pool_n']}-batch device pool "
+                                    f"({head['pool_n'] * head['img_bytes'] >> 20} MiB > L2)"},
+            "clocks": head["clocks"], "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "final_loss": head["final_loss"],
+            "other_configs": other,
         }
-        line["config"]["tokens"] = (w["image"] // w["patch"]) ** 2 + 1
         print(json.dumps(line), flush=True)
     if world > 1:
-        # The captured graph holds NCCL work; drop it before tearing the communicator down, and do not let a slow
-        # communicator abort keep the rank alive after the result line has been printed.
+        # Captured graphs held NCCL work; they are dropped in measure().  Do not let a slow communicator abort keep the rank
+        # alive after the result line has been printed.
         dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
-        trainer._graph = None
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
       store_split8_3(img + IMG_DO * CH, img + (IMG_DO + 4) * CH, img + (IMG_DO + 8) * CH, (uint32_t)part * CH + rowoff, d);
     }
     publish();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, COL_G, IMG_DO, IMG_DO + 4, IMG_DO + 8, 2, W2B, 256, 128, 512, x192, x128, x64);  // dh raw -> [0,192)
       commit(&bar_g);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
     }
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, COL_G, IMG_A, IMG_A + 6, A_LO2, 2, WPF, 2 * 1536, 1536, 128, f96, f64, f32);     // p -> [0, 96)
       commit(&bar_g);
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
       store_split8_3(img + IMG_N * CH, img + (IMG_N + 6) * CH, img + N_LO2 * CH, (uint32_t)part * CH + rowoff, n2);
     }
     publish();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, COL_G, IMG_N, IMG_N + 6, N_LO2, 2, W1F, 2 * 3072, 3072, 128, f192, f128, f64);   // h -> [0, 192)
       commit(&bar_g);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
                      (uint32_t)(2 * part + half) * CH + rowoff, dh);
     }
     publish();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, COL_G, IMG_DH, IMG_DH + 8, IMG_DH + 16, 4, W1B, 256, 128, 1024, x96, x64, x32);  // dn -> [0, 96)
       commit(&bar_g);
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
       store_split8_3(img + IMG_DP * CH, img + (IMG_DP + 4) * CH, img + (IMG_DP + 8) * CH, (uint32_t)part * CH + rowoff, dp);
     }
     publish();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, COL_G + 96, IMG_DP, IMG_DP + 4, IMG_DP + 8, 2, WPB, 256, 128, 512, x96, x64, x32);  // da -> [96, 192)
       commit(&bar_g);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_fwd_tc_kernel(const MlpArgs
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       issue();
       commit(&bar_g);
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_fwd_tc_kernel(const LnQk
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, 0, Q_N, Q_N + 4, Q_N + 8, 2, Q_W, 2 * 2304, 2304, 128, f144, f96, f48);              // outputs 0..47
       tc_row_product3(cx, 144, Q_N, Q_N + 4, Q_N + 8, 2, Q_W + Q_WHALF, 2 * 2304, 2304, 128, f144, f96, f48);  // outputs 48..95
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_bwd_tc_kernel(const LnQk
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, 0, B_DQ, B_DQ + 12, B_DQ + 24, 6, B_W, 256, 128, 1536, x96, x64, x32);  // dn -> cols [0, 96)
       commit(&bar_g);
@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) embed_fwd_tc_kernel(const Embed
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_row_product3(cx, 0, E_A, E_A + 8, E_A + 16, (p.PD + 15) / 16, E_W, 2 * 1536, 1536, 128, f96, f64, f32);
       commit(&bar_g);
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) embed_bwd_tc_kernel(const Embed
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       tc_token_reduction(cx, 0, EB_DO, EB_DO + 4, EB_P, w144, w80, first);
       commit(&bar_w);

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
         fence_before_sync();
         __syncthreads();
         // ---- G1: P = x W^T, three TF32 terms
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           fence_after_sync();
           bool acc = false;
 #pragma unroll
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
         fence_smem_to_async();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           fence_after_sync();
           if (pass == 0) {  // G2: S[rb] (+)= phi^T [v|1], terms hi*hi + hi*lo + lo*hi
             const uint8_t* v1 = vreg + (uint32_t)(tile & 1) * 2 * vbytes;

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     }
     fence_before_sync();
     __syncthreads();  // every thread holds its P values: the P columns may be overwritten
-    if (q == 0 && tid == 0) {
+    if (q == 0 && warp == 0 && elect_one()) {
       fence_after_sync();
       issue_g1();  // queries (their x images were written before the barrier)
     }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     fence_before_sync();
     __syncthreads();
     // ---- G1 (keys)
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       issue_g1();
     }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     fence_before_sync();
     __syncthreads();
     // ---- G2: S(pair, rb) = phi_k^T [v|1]
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       for (int sp = 0; sp < 2; ++sp)
         for (int rb = 0; rb < nrb; ++rb) {
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_fwd_kernel(const LaTcArg
     fence_before_sync();
     __syncthreads();
     // ---- G4: [num_A | num_B] = phi_q [S_A | S_B]
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       fence_after_sync();
       for (int s = 0; s < Mp / 16; ++s) {
         const uint64_t bd = make_desc(smem_u32(vs) + (uint32_t)s * 256, 128, s_ch);

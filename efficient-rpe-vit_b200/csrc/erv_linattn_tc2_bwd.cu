@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       } else {
       TR(pass * 100 + 1);
       // ---- G1: P = x W^T (3xTF32)
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         fence_after_sync();
         bool acc = false;
 #pragma unroll
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       }
       fence_before_sync();
       __syncthreads();  // all P reads are done: the P columns may be overwritten (dphi)
-      if (pass == 2 && tid == 0) {  // K2: dphi_k = v [dS_A ; dS_B]^T can start as soon as P has been consumed
+      if (pass == 2 && warp == 0 && elect_one()) {  // K2: dphi_k = v [dS_A ; dS_B]^T can start as soon as P has been consumed
         fence_after_sync();
         bool acc = false;
         for (int sp = 0; sp < 2; ++sp)
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           fence_smem_to_async();
           fence_before_sync();
           __syncthreads();
-          if (tid == 0) {
+          if (warp == 0 && elect_one()) {
             fence_after_sync();
             issue_accumulate(hb);
           }
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         fence_smem_to_async();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           fence_after_sync();
           issue_accumulate(0);
           // dphi_q for the whole row, into the (consumed) P columns: K = [pair A's 16 | pair B's 16]
@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           fence_smem_to_async();
           fence_before_sync();
           __syncthreads();
-          if (tid == 0) {
+          if (warp == 0 && elect_one()) {
             fence_after_sync();
             issue_accumulate(1);
           }
@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           fence_smem_to_async();
           fence_before_sync();
           __syncthreads();
-          if (tid == 0) {
+          if (warp == 0 && elect_one()) {
             fence_after_sync();
             for (int s = 0; s < HF / 16; ++s) {
               const uint64_t bd = make_desc(smem_u32(simg) + (uint32_t)(hb * (HF / 16) + s) * 256, 128, s_ch);

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         __syncthreads();
         TR(pass * 100 + 1);
         // ---- G1: P = x W^T (3xTF32)
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           fence_after_sync();
           bool acc = false;
 #pragma unroll
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           fence_before_sync();
           __syncthreads();  // all P reads are done: the P columns may be overwritten (dphi)
         }
-        if (pass == 2 && tid == 0) {  // K2: dphi_k = [v|1] [dS|dz]^T can start as soon as P has been consumed
+        if (pass == 2 && warp == 0 && elect_one()) {  // K2: dphi_k = [v|1] [dS|dz]^T can start as soon as P has been consumed
           fence_after_sync();
           bool acc = false;
           for (int term = 0; term < 3; ++term) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           fence_smem_to_async();
           fence_before_sync();
           __syncthreads();
-          if (tid == 0) {
+          if (warp == 0 && elect_one()) {
             fence_after_sync();
             bool acc = !first;
             for (int term = 0; term < 3; ++term) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           for (int hb = 0; hb < nrb; ++hb) {
             store_half(hb);
             accumulate_half(hb, n0 == 0);
-            if (tid == 0) commit(&bar_b);
+            if (warp == 0 && elect_one()) commit(&bar_b);
             mbar_wait(&bar_b, ph_b);
             ph_b ^= 1;
             fence_after_sync();
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           for (int hb = 0; hb < nrb; ++hb) {
             store_half(hb);
             accumulate_half(hb, n0 == 0);
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
               if (hb == nrb - 1) {  // dphi_q for the whole row, into the (consumed) P columns
                 bool acc = false;
                 for (int term = 0; term < 3; ++term) {

@@ -72,6 +72,9 @@ SIGNATURES = {
     "erv_debug_umma_gemm": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "erv_debug_set_trace": (None, [_P]),
     "erv_debug_umma_timing": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
+    "erv_debug_umma_gemm_ts": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "erv_debug_umma_timing2": (c_int, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "erv_debug_unit_probe": (c_int, [_I, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

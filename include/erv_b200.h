@@ -262,6 +262,18 @@ int erv_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, 
 void erv_debug_set_trace(long long* device_buffer);
 int erv_debug_umma_timing(int N, int bf16, int a_mn_major, int b_mn_major, int iters, long long* cycles,
                           void* stream);
+/* The same product with the A operand in tensor memory (written with tcgen05.st, lane = row): pins the TMEM operand
+ * layout of the kernels that keep their feature tiles out of shared memory. */
+int erv_debug_umma_gemm_ts(const float* A, const float* B, float* D, int N, int K, int b_mn_major, int bf16,
+                           void* stream);
+/* MMA cost with `nacc` independent accumulators, M = 64 or 128, A from shared (0) or tensor (1) memory.
+ * elected: 1 = issued by the elected lane of a converged warp (elect.sync), 0 = by a divergent `tid == 0`.
+ * cycles[0] = first issue -> completion, cycles[1] = issue loop alone (device int64[2]). */
+int erv_debug_umma_timing2(int N, int M, int bf16, int a_tmem, int b_mn_major, int nacc, int iters, int elected,
+                           long long* cycles, void* stream);
+/* One-SM throughput probes: mode 0 tcgen05.ld, 1 tcgen05.st, 2 cvt.rn.bf16x2.f32, 3 ex2.approx, 4 both, 5 FFMA.
+ * cycles[0] = SM clocks for `iters` instructions per thread; sink: >= 512 floats or NULL. */
+int erv_debug_unit_probe(int mode, int threads, int iters, long long* cycles, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

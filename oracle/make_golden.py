@@ -34,7 +34,12 @@ SHAPES = {
     "a": (2, 17, 32, 2, None),    # reference default dims, MNIST/CIFAR p8 token count, M=44
     "b": (3, 26, 64, 2, 64),      # Dh=32
     "c": (1, 65, 64, 1, 72),      # Dh=64 (one head), CIFAR p4 token count
+    # shapes that dispatch to the tcgen05 kernels (Dh = 16): BASELINE config 2 (N=65, M=256: two pairs per tile) and
+    # config 4 (N=197, M=44: one pair per 128-token tile, two token tiles); fp32 and bf16-autocast arms
+    "d": (2, 65, 32, 2, 256),
+    "e": (2, 197, 32, 2, 44),
 }
+ONLY = [a for a in sys.argv[1:] if a in SHAPES]  # e.g. `python oracle/make_golden.py d e` adds shapes without touching the rest
 
 
 def np32(t):
@@ -66,14 +71,39 @@ def attention_cases():
                 if a == "softmax" and r == "most_general":
                     continue
                 seed += 1
-                attn, rpe = build(a, r, n, dim, heads, m, seed)
-                attn.eval()
-                x = torch.randn(b, n, dim, requires_grad=True)
-                w = torch.randn(b, n, dim)  # cotangent
-                out = attn(x, rpe=rpe)
-                (out * w).sum().backward()
+                if ONLY and sname not in ONLY:
+                    continue
+                # ReLU features are not differentiable where a projection crosses zero: a pre-activation within rounding
+                # distance of 0 makes the REFERENCE's own gradient jump under a 1e-6 perturbation of its input, and no
+                # implementation can be asked to reproduce that.  Shapes added in round 2 (d, e) are screened: the reference's
+                # dx must move by < 1e-4 (rel-L2) under 2e-6 relative perturbations (smooth cases move by ~1e-5), else the case is re-seeded (recorded in the file).
+                case_seed, reseeds = seed, 0
+                while True:
+                    attn, rpe = build(a, r, n, dim, heads, m, case_seed)
+                    attn.eval()
+                    x = torch.randn(b, n, dim, requires_grad=True)
+                    w = torch.randn(b, n, dim)  # cotangent
+                    out = attn(x, rpe=rpe)
+                    (out * w).sum().backward()
+                    if sname not in ("d", "e"):
+                        break
+                    drift = 0.0
+                    for _ in range(3):  # three draws of a 2e-6 relative perturbation (what a different rounding of the rotation does)
+                        x_p = (x.detach() * (1.0 + 2e-6 * torch.randn(b, n, dim))).requires_grad_(True)
+                        (attn(x_p, rpe=rpe) * w).sum().backward()
+                        drift = max(drift, float((x_p.grad - x.grad).norm() / x.grad.norm()))
+                    for p_ in list(attn.parameters()) + (list(rpe.parameters()) if rpe is not None else []):
+                        p_.grad = None
+                    if drift < 1e-4:
+                        x.grad = None
+                        out = attn(x, rpe=rpe)
+                        (out * w).sum().backward()
+                        break
+                    reseeds += 1
+                    print(f"  {sname} {a} {r}: reference dx drifts {drift:.1e} under 2e-6 input perturbations (kink); re-seeding")
+                    case_seed += 100000
                 rec = {"x": np32(x), "cotangent": np32(w), "out": np32(out), "dx": np32(x.grad),
-                       "heads": np.int64(heads)}
+                       "heads": np.int64(heads), "seed": np.int64(case_seed)}
                 for k, v in attn.state_dict().items():
                     rec["attn." + k] = v.numpy()
                 for k, p in attn.named_parameters():
@@ -183,5 +213,6 @@ def model_cases():
 
 if __name__ == "__main__":
     attention_cases()
-    unit_cases()
-    model_cases()
+    if not ONLY:
+        unit_cases()
+        model_cases()
