@@ -39,9 +39,15 @@ cudaError_t ensure_smem(const void* fn, size_t bytes) {
 //   g = grad * grad_scale (+ wd * p when not decoupled);  p *= 1 - lr*wd when decoupled
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
 //   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// hyper (optional, device): [lr, beta1, beta2, eps, weight_decay] read at run time, so a captured CUDA graph follows a
+// learning-rate schedule (the by-value arguments are baked into the graph at capture).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            int decoupled, float gscale, int64_t step, const int64_t* __restrict__ step_dev) {
+                            int decoupled, float gscale, int64_t step, const int64_t* __restrict__ step_dev,
+                            const float* __restrict__ hyper) {
+  if (hyper != nullptr) {
+    lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4];
+  }
   const int64_t t = step_dev ? *step_dev : step;
   const float bc1 = 1.f - powf(b1, (float)t);
   const float bc2s = sqrtf(1.f - powf(b2, (float)t));
@@ -80,7 +86,20 @@ extern "C" int erv_adam_step(float* param, const float* grad, float* exp_avg, fl
   if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                   beta2, eps, weight_decay, decoupled_wd, grad_scale,
-                                                                  step, step_dev);
+                                                                  step, step_dev, nullptr);
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
+
+extern "C" int erv_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                                 const float* hyper, int decoupled_wd, float grad_scale, const int64_t* step_dev,
+                                 void* stream) {
+  ERV_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper && step_dev, "erv_adam_step_dev: null pointer");
+  if (n == 0) return ERV_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, 0.f, 0.f, 0.f, 0.f,
+                                                                  0.f, decoupled_wd, grad_scale, 0, step_dev, hyper);
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }

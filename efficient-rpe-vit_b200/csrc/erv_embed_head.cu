@@ -135,8 +135,11 @@ __global__ void __launch_bounds__(256) head_loss_fwd_kernel(const HeadArgs p) {
   }
   const float mx = warp_max(logit);
   const float se = warp_sum(lane < p.K ? expf(logit - mx) : 0.f);
-  const float picked = __shfl_sync(0xffffffffu, logit, (int)p.labels[s]);
-  if (lane == 0) p.rows[s] = (mx + logf(se)) - picked;
+  // a label outside [0, K) (F.cross_entropy raises for it) makes this sample's loss NaN instead of reading another lane
+  const long long lab = p.labels[s];
+  const bool lab_ok = lab >= 0 && lab < (long long)p.K;
+  const float picked = __shfl_sync(0xffffffffu, logit, lab_ok ? (int)lab : 0);
+  if (lane == 0) p.rows[s] = lab_ok ? (mx + logf(se)) - picked : __int_as_float(0x7fc00000);
 }
 // loss = mean of rows, fixed order (one warp)
 __global__ void __launch_bounds__(32) head_loss_mean_kernel(const float* __restrict__ rows, float* loss, int B) {

@@ -474,11 +474,12 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
     return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, state, st);
   if (!bwd && la_tc_eligible(N, DH, M))
     return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
-  if (bwd && la_tc_eligible(N, DH, M) && getenv("ERV_DISABLE_TC_BWD") == nullptr) {
+  static const bool tc_bwd_off = getenv("ERV_DISABLE_TC_BWD") != nullptr, tc2_bwd_off = getenv("ERV_DISABLE_TC2_BWD") != nullptr;
+  if (bwd && la_tc_eligible(N, DH, M) && !tc_bwd_off) {
     const int slots = la_slots(B, H);
     float* dgp = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;
     if (dgp) ERV_CUDA(cudaMemsetAsync(dgp, 0, (size_t)H * slots * N * DH * sizeof(float), st));
-    if (la_tc2_eligible(N, DH, M) && getenv("ERV_DISABLE_TC2_BWD") == nullptr)
+    if (la_tc2_eligible(N, DH, M) && !tc2_bwd_off)
       return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
     return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
   }

@@ -7,7 +7,8 @@
 //   Q   P = q W^T ; phi_q ; den = phi_q . z ; a = [dO/den | -(dO.O)/den]
 //       dS_pair = phi_q^T a                                                               tcgen05, S's TMEM columns
 //       dphi_q  = a S^T  (both pairs in one K = 32 product: block-structured a image)     tcgen05, P's TMEM columns
-//       + a16 z^T (rank 1, registers) ; G = dphi (.) dphi/dP ; dq = G [W^T|1] ...          fp32 FMAs
+//       + a16 z^T (rank 1, registers) ; G = dphi (.) dphi/dP, written back over the consumed dphi columns as bf16 hi/lo
+//       dq' = G [W^T|1]   (A operand read from tensor memory, K = features)             tcgen05, 48 spare TMEM columns
 //   K2  P = k W^T ; phi_k ; dphi_k = v dS^T (+ dz) ; dv = phi_k [dS_A|dS_B]                tcgen05 ; dk as dq
 // bf16 hi/lo splits of both operands keep the contractions at ~2^-17; a split product takes two instructions by
 // concatenating along N: phi_hi x [b_hi | b_lo] and phi_lo x b_hi.  The feature images are written one 128-feature half
@@ -128,14 +129,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   constexpr int DH = 16, RW = DH + 4;
   using C = TcCfg<DH>;
   constexpr int nrb = NRB, HF = CPH * 32, FPH = CPH * 8, Mp = NRB * HF, NC = NRB * CPH;
-  constexpr uint32_t COL_P = 0, COL_S = 256, S_STRIDE = 64;
+  constexpr uint32_t COL_P = 0, COL_S = 256, S_STRIDE = 48, COL_DQ = 448;  // [448, 496): G [W^T|1] of the running sweep
   constexpr uint32_t wbytes = (uint32_t)(Mp / 8) * (DH / 4) * 128;
   constexpr uint32_t s_ch = (uint32_t)(Mp / 8) * 128;
   constexpr uint32_t halfbytes = 16 * kTokCh;  // one feature half, padded to 128 rows of the M dimension
   constexpr uint32_t avbytes = 12 * kTokCh;    // per pair side: [hi(2) | special(1) | zero(1) | lo(2)] chunks
 
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_a, bar_b, bar_c;  // G1 / token- and feature-contractions / dphi
+  __shared__ __align__(8) uint64_t bar_a, bar_b, bar_c, bar_d;  // G1 / token- and feature-contractions / dphi / G [W^T|1]
   __shared__ uint32_t tmem_base_s;
   __shared__ float n2_s[128];
   __shared__ float ex_s[4][128];   // row-max exchange
@@ -175,10 +176,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   uint8_t* xl = xh + C::X_BYTES;
   uint8_t* phi1 = xl + C::X_BYTES;  // one feature half [128 tokens x 128 features], hi
   uint8_t* phi2 = phi1 + halfbytes;  // lo
-  float* red = reinterpret_cast<float*>(phi1);  // [3][128][RW] fp32, aliases the feature images when they are idle
   uint8_t* av = phi2 + halfbytes;    // [v|1] or [a|a16] rows, block-structured over the two pair sides
   uint8_t* simg = av + avbytes;      // [S_A|S_B] hi, lo then [dS_A|dS_B]: byte(f, j) = (j/8)*s_ch + (f/8)*128 + (f%8)*16 + (j%8)*2
-  float* w32 = reinterpret_cast<float*>(simg + 8 * s_ch);  // [Mp][RW] fp32: W^T rows, column DH = 1 (rowsum)
+  // [W^T | 1 | 0 | W^T lo] as a bf16 MN-major B operand (K = features): byte(f, j) = (j/8)*s_ch + (f/8)*128 + (f%8)*16 + (j%8)*2,
+  // columns j: [0,16) hi, 16 = ones (row sum of G), [32,48) lo
+  uint8_t* wimg = simg + 8 * s_ch;
 
   // chunk c of this thread: half c / CPH, local chunk c % CPH
   auto feat0 = [&](int c) { return (c / CPH) * HF + part * FPH + (c % CPH) * 8; };
@@ -190,10 +192,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
     mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
     mbar_init(&bar_c, 1);
+    mbar_init(&bar_d, 1);
     mbar_init_fence();
   }
-  {  // W^T of this head: hi/lo TF32 images (rows f, K = Dh) and the fp32 rows [W^T | 1]
+  {  // W^T of this head: hi/lo TF32 images (rows f, K = Dh) and the bf16 [W^T | 1 | 0 | W^T lo] image
     const float* om = p.omega + (size_t)h * DH * M;
+    for (int i = tid; i < (int)(6 * s_ch / 16); i += kTcThreads) reinterpret_cast<uint4*>(wimg)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     for (int i = tid; i < Mp * DH; i += kTcThreads) {
       const int d = i / Mp, f = i % Mp;
       const float w = (f < M) ? __ldg(om + (size_t)d * M + f) : 0.f;
@@ -201,11 +206,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
       const uint32_t off = off_kmajor(f, d, 4, 4, C::X_LBO, C::X_SBO);
       *reinterpret_cast<float*>(wh + off) = hi;
       *reinterpret_cast<float*>(wl + off) = lo;
-      w32[f * RW + d] = w;
-    }
-    for (int i = tid; i < Mp * 4; i += kTcThreads) {
-      const int f = i >> 2, j = DH + (i & 3);
-      w32[f * RW + j] = (j == DH && f < M) ? 1.f : 0.f;
+      const __nv_bfloat16 bh = __float2bfloat16_rn(w), bl = __float2bfloat16_rn(w - __bfloat162float(bh));
+      const uint32_t fo = (uint32_t)(f >> 3) * 128 + (f & 7) * 16;
+      *reinterpret_cast<__nv_bfloat16*>(wimg + (uint32_t)(d >> 3) * s_ch + fo + (d & 7) * 2) = bh;
+      *reinterpret_cast<__nv_bfloat16*>(wimg + (uint32_t)(4 + (d >> 3)) * s_ch + fo + (d & 7) * 2) = bl;
+      if (d == 0) *reinterpret_cast<__nv_bfloat16*>(wimg + 2 * s_ch + fo) = __float2bfloat16_rn(f < M ? 1.f : 0.f);
     }
   }
   fence_smem_to_async();
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   fence_after_sync();
   const uint32_t tm = tmem_base_s;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  uint32_t ph_a = 0, ph_b = 0, ph_c = 0;
+  uint32_t ph_a = 0, ph_b = 0, ph_c = 0, ph_d = 0;
   int tr_i = 0;
   // phase trace (tools/trace_bwd.py): compiled in only with -DERV_TRACE, so the production kernel carries no checks
 #ifdef ERV_TRACE
@@ -240,6 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
   const uint32_t idesc_dphi = make_idesc(FMT_BF16, 128, Mp, false, false);  // dphi = rows [S_A ; S_B]^T
   const uint32_t idesc_dv64 = make_idesc(FMT_BF16, 128, 64, false, true);   // dv = phi [dS_A|dS_B]
   const uint32_t idesc_dv32 = make_idesc(FMT_BF16, 128, 32, false, true);
+  const uint32_t idesc_dq48 = make_idesc(FMT_BF16, 128, 48, false, true);   // dq' = G [W^T|1|0|W^T lo], A from tensor memory
+  const uint32_t idesc_dq32 = make_idesc(FMT_BF16, 128, 32, false, true);
   const float kLog2e = 1.4426950408889634f;
   const float log2_c = log2f(p.inv_sqrt_m);
   const uint32_t rowoff = (uint32_t)(row >> 3) * 128 + (row & 7) * 16;
@@ -508,6 +515,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
           }
         }
       }
+      // W^T row f (fp32 to ~21 bits) from the TF32 hi/lo images
+      auto load_w_row = [&](int f, float (&wr)[DH]) {
+        const uint32_t wo = (uint32_t)(f >> 3) * C::X_SBO + (f & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 a = ld4(reinterpret_cast<const float*>(wh + wo + c * C::X_LBO));
+          const float4 l = ld4(reinterpret_cast<const float*>(wl + wo + c * C::X_LBO));
+          wr[4 * c] = a.x + l.x; wr[4 * c + 1] = a.y + l.y; wr[4 * c + 2] = a.z + l.z; wr[4 * c + 3] = a.w + l.w;
+        }
+      };
       // ---- end of sweep: move the TMEM accumulator (S after K1, dS after Q) into the bf16 images; lone-token terms
       auto sweep_tail = [&](const bool from_state, const float (&st)[DH + 1]) {
         TR(pass * 100 + 20);
@@ -571,10 +588,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
             for (int d = 0; d < DH; ++d) dph = fmaf(lone_do[sp][d] * r, sv[d], dph);
             const float gq = own ? (favor ? dph * pq : (pq > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
-            const float* wr = w32 + (own ? f : 0) * RW;
+            float wr[DH];
+            load_w_row(own ? f : 0, wr);
             float a32[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a32[j] = (j <= DH) ? gq * wr[j] : 0.f;
+            for (int j = 0; j < 32; ++j) a32[j] = (j < DH) ? gq * wr[j] : (j == DH ? gq : 0.f);
             const float t = warp_sum32(a32);  // lane j: warp total of partial j
             if (lane <= DH) red2_s[warp][lane] = t;
             if ((tid & 255) == 0) {
@@ -587,7 +605,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
 #pragma unroll
             for (int d = 0; d < DH; ++d) dph = fmaf(lone_v[sp][d], sv[d], dph);
             const float gk = own ? (favor ? dph * pk : (pk > 0.f ? dph * p.inv_sqrt_m : 0.f)) : 0.f;
-            const float* wr = w32 + (own ? f : 0) * RW;
+            float wr[DH];
+            load_w_row(own ? f : 0, wr);
             float a32[32];  // [0, DH): dv of the lone key, [DH, 2 DH): G [W^T] ; the row sum goes separately
 #pragma unroll
             for (int d = 0; d < DH; ++d) {
@@ -596,7 +615,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
             }
             const float t = warp_sum32(a32);
             red3_s[warp][lane] = t;
-            const float t2 = warp_sum(gk * wr[DH]);
+            const float t2 = warp_sum(gk);
             if (lane == 0) red3_s[warp][2 * DH] = t2;
           }
         }
@@ -730,56 +749,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         }
         commit(&bar_b);
       };
-      // 4-way reduction over the threads of a row; result valid in part 0
-      auto reduce_rows = [&](float (&acc)[RW]) {
-        if (part > 0) {
+      // G (in pr) -> bf16 hi/lo, written over the dphi columns THIS thread has just consumed (its features of half hb sit in the
+      // FPH fp32 columns [hb*HF + part*FPH, +FPH): hi words go to the first FPH/2 of them, lo words to the rest), so no other
+      // thread's unread dphi is touched.  Then dq' = G [W^T|1] on the tensor pipe with A read from tensor memory: k-step
+      // (hb, part, j) covers features hb*HF + part*FPH + 16 j.
+      auto store_g_tmem = [&]() {
 #pragma unroll
-          for (int j = 0; j < RW; j += 4)
-            st4(red + ((size_t)(part - 1) * 128 + row) * RW + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
-        }
-        __syncthreads();
-        if (part == 0) {
+        for (int hb = 0; hb < NRB; ++hb)
 #pragma unroll
-          for (int q = 0; q < 3; ++q)
+          for (int cc = 0; cc < CPH; cc += 2) {
+            uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int j = 0; j < RW; j += 4) {
-              const float4 v = ld4(red + ((size_t)q * 128 + row) * RW + j);
-              acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
-            }
-        }
-      };
-      // G (in pr) x [W^T | 1]: this thread's partial sums
-      auto gradient_partial = [&](float (&acc)[RW]) {
-        // packed pairs: FFMA2 halves the issue slots of the loop; what bounds it is the shared-memory reads of the W^T rows,
-        // so the ones column (row sum of G; padded features carry G = 0) is a plain add instead of a fifth 128-bit load
-        unsigned long long a2[DH / 2];
-        float ones_a = 0.f, ones_b = 0.f;
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
-        for (int j = 0; j < DH / 2; ++j) a2[j] = 0ull;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int f0 = feat0(c);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float gq = __uint_as_float(pr[c][i]);
-            const float* wr = w32 + (f0 + i) * RW;
-#pragma unroll
-            for (int cd = 0; cd < DH / 4; ++cd) {
-              const float4 a = ld4(wr + 4 * cd);
-              ffma2(a2[2 * cd], gq, a.x, a.y);
-              ffma2(a2[2 * cd + 1], gq, a.z, a.w);
-            }
-            if (i & 1) ones_b += gq; else ones_a += gq;
+              for (int i = 0; i < 4; ++i)
+                split_pack2(__uint_as_float(pr[hb * CPH + cc + e][2 * i]), __uint_as_float(pr[hb * CPH + cc + e][2 * i + 1]),
+                            hw[4 * e + i], lw[4 * e + i]);
+            const uint32_t col = tm + lane_off + COL_P + (uint32_t)(hb * HF + part * FPH + cc * 4);
+            tmem_st8(col, hw);
+            tmem_st8(col + FPH / 2, lw);
           }
-        }
+        tmem_wait_st();
+      };
+      auto issue_g_product = [&]() {  // one elected thread
+        bool acc = false;
+        for (int hb = 0; hb < NRB; ++hb)
+          for (int pq = 0; pq < 4; ++pq)
+            for (int j = 0; j < FPH / 16; ++j) {
+              const uint32_t fs = (uint32_t)(hb * HF + pq * FPH + 16 * j);
+              const uint32_t ca = tm + COL_P + (uint32_t)(hb * HF + pq * FPH + 8 * j);
+              const uint64_t bd = make_desc(smem_u32(wimg) + fs * 16, 128, s_ch);
+              mma_f16_ts(tm + COL_DQ, ca, bd, idesc_dq48, acc);
+              mma_f16_ts(tm + COL_DQ, ca + FPH / 2, bd, idesc_dq32, true);
+              acc = true;
+            }
+        commit(&bar_d);
+      };
+      // dq' (TMEM) -> this row's 17 sums; valid in part 0
+      auto load_g_product = [&](float (&acc)[RW]) {
+        if (part == 0) {
+          float d0[32], d1[16];
+          tmem_ld32(tm + lane_off + COL_DQ, d0);
+          tmem_ld16(tm + lane_off + COL_DQ + 32, d1);
 #pragma unroll
-        for (int j = 0; j < DH / 2; ++j) {
-          acc[2 * j] = lo_of(a2[j]);
-          acc[2 * j + 1] = hi_of(a2[j]);
+          for (int d = 0; d < DH; ++d) acc[d] = d0[d] + d1[d];
+          acc[DH] = d0[DH];
         }
-        acc[DH] = ones_a + ones_b;
-#pragma unroll
-        for (int j = DH + 1; j < RW; ++j) acc[j] = 0.f;
       };
       // reduced sums (part 0) -> gradient wrt the raw q/k row, written to global memory
       auto store_input_gradient = [&](const float (&acc)[RW]) {
@@ -899,21 +914,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         fence_after_sync();
         TR(108);
         load_dphi_to_g(&z_s[side][0], a16_s[row]);
-        fence_before_sync();
         TR(109);
-        float acc[RW];
-        gradient_partial(acc);
+        store_g_tmem();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {
+          fence_after_sync();
+          issue_g_product();
+        }
         TR(110);
         if (nrb > 1) {
-          mbar_wait(&bar_b, ph_b);  // the second half's contraction has read the feature images: red may alias them
+          mbar_wait(&bar_b, ph_b);  // the second half's contraction has completed
           ph_b ^= 1;
           fence_after_sync();
         }
-        reduce_rows(acc);
-        TR(111);
-        store_input_gradient(acc);
         prefetch(g, 2);
-        TR(112);
+        TR(111);
       } else {
         // ---- K2: dv = phi_k [dS_A|dS_B] ; dphi_k (already issued) ; dk
         for (int hb = 0; hb < nrb; ++hb) {
@@ -942,18 +958,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
         fence_after_sync();
         TR(208);
         load_dphi_to_g(&dz_s[side][0], 1.0f);
-        fence_before_sync();
         TR(209);
-        float acc[RW];
-        gradient_partial(acc);
+        store_g_tmem();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {
+          fence_after_sync();
+          issue_g_product();
+        }
         TR(210);
         mbar_wait(&bar_b, ph_b);
         ph_b ^= 1;
         fence_after_sync();
-        reduce_rows(acc);
         TR(211);
-        store_input_gradient(acc);
-        TR(212);
         prefetch(g + gridDim.x, 0);
         if (part == 0) {  // dv rows: hi-part + lo-part columns of this row's pair
           float a0[16], a1[16];
@@ -967,13 +984,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc2_bwd_kernel(const LaTc2Bw
                                            a0[4 * c + 3] + a1[4 * c + 3]));
           }
         }
+        {  // dk' = G [W^T|1]
+          mbar_wait(&bar_d, ph_d);
+          ph_d ^= 1;
+          fence_after_sync();
+          float acc[RW];
+          load_g_product(acc);
+          store_input_gradient(acc);
+          TR(212);
+        }
         fence_before_sync();
-        __syncthreads();  // red (feature images) and the TMEM columns are reused by the next group
+        __syncthreads();  // the feature images and the TMEM columns are reused by the next group
         TR(213);
       }
         if (pass < 2) {
           const float none[DH + 1] = {};
           sweep_tail(false, none);
+        }
+        if (pass == 1) {  // dq' ran on the tensor pipe under the sweep tail
+          mbar_wait(&bar_d, ph_d);
+          ph_d ^= 1;
+          fence_after_sync();
+          float acc[RW];
+          load_g_product(acc);
+          store_input_gradient(acc);
+          fence_before_sync();
+          TR(112);
         }
       }
     }
@@ -989,7 +1025,7 @@ size_t la_tc2_bwd_smem_bytes(int M) {
   const int Mp = tc2b_mp(M);
   const size_t wbytes = (size_t)(Mp / 8) * 4 * 128, xbytes = 16 * 4 * 128;
   return 2 * wbytes + 2 * xbytes + 2 * 16 * (size_t)kTokCh + 12 * (size_t)kTokCh + 8 * (size_t)(Mp / 8) * 128 +
-         (size_t)Mp * 20 * sizeof(float) + 128;
+         6 * (size_t)(Mp / 8) * 128 + 128;
 }
 
 int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,

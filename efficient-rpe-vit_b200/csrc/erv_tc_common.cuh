@@ -117,16 +117,20 @@ __device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const f
   }
 }
 
-// ---- bf16 hi/lo splitting without conversion instructions (the XU pipe is busy with ex2) --------------------
-// hi = upper 16 bits of the fp32 pattern (truncation), lo = upper 16 bits of (v - hi); hi + lo carries >= 16
-// significant bits.  Two values are packed per 32-bit word with one byte-permute each.
+// ---- bf16 hi/lo splitting ---------------------------------------------------------------------------------------
+// hi = bf16(v) and lo = bf16(v - hi), both round-to-nearest, two values per 32-bit word: hi + lo carries >= 16 significant bits
+// (|v - hi| <= 2^-9 |v| is exact in fp32, its own rounding error is <= 2^-18 |v|).  Six instructions per pair of values:
+// two F2FP.BF16.F32.PACK_AB, a shift, a mask and two subtractions.  F2FP runs at 32 lanes/clk/SM on a pipe of its own: it does
+// not compete with MUFU.EX2 (profiles/r02_tcgen05_issue_cost.md), unlike the round-1 integer version (eight ALU instructions).
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo_half, float hi_half) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+  return r;
+}
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-  const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
-  hi = __byte_perm(ua, ub, 0x7632);
-  // the low part is rounded to nearest (magnitude half-up: + 0x8000 before the truncation) so the split error is
-  // unbiased and <= 2^-17 relative; plain truncation leaves a one-sided 2^-16
-  lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
+  hi = pack_bf16x2_rn(a, b);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2_rn(ra, rb);
 }
 __device__ __forceinline__ void store_split8(uint8_t* img_hi, uint8_t* img_lo, uint32_t off, const float (&v)[8]) {
   uint4 h, l;

@@ -63,6 +63,7 @@ SIGNATURES = {
     "erv_toeplitz_matmul_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_toeplitz_matmul_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_adam_step": (c_int, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _I, _F, c_int64, _P, _P]),
+    "erv_adam_step_dev": (c_int, [_P, _P, _P, _P, _Z, _P, _I, _F, _P, _P]),
     "erv_linear_wgrad_supported": (c_int, [_I, _I, _I]),
     "erv_linear_wgrad_workspace": (c_size_t, [_I, _I, _I]),
     "erv_linear_wgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
@@ -119,10 +120,17 @@ def check(status: int, what: str = ""):
 
 
 def require_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: the C ABI launches on torch's current stream of the current
+    device (stream()), and the per-function shared-memory attributes are cached per device."""
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("erv_b200 runs on CUDA tensors only (sm_100a); got a tensor on "
                                f"'{t.device}'. There is no CPU fallback.")
+        if t.device.index != torch.cuda.current_device():
+            raise RuntimeError(f"erv_b200: tensor on {t.device} but the current device is cuda:{torch.cuda.current_device()}; "
+                               "wrap the call in `with torch.cuda.device(tensor.device):`")
 
 
 def ptr(t):

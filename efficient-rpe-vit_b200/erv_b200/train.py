@@ -18,13 +18,37 @@ from . import ops
 from .parallel import FlatParams, world_size
 
 
+class _ParamGroup(dict):
+    """torch.optim-style parameter group: `for g in trainer.param_groups: g["lr"] = x` reaches the device-resident
+    hyper-parameters (and therefore a step that has already been captured in a CUDA graph)."""
+
+    def __init__(self, trainer, **kw):
+        super().__init__(**kw)
+        self._trainer = trainer
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        if key in ("lr", "betas", "eps", "weight_decay"):
+            self._trainer._set_hyper(**{key: value})
+
+
 class Trainer:
+    """Hyper-parameters live in a 5-float device tensor `[lr, beta1, beta2, eps, weight_decay]` that the fused Adam kernel
+    reads at run time (erv_adam_step_dev), so `trainer.lr = x`, `trainer.set_lr(x)` or `param_groups[0]["lr"] = x` take effect
+    on the next step whether or not the step has been captured.  torch's LR schedulers insist on a torch.optim.Optimizer, so
+    a schedule is attached as a plain callable instead: `trainer.lr_schedule = lambda step: ...` is evaluated on the host
+    before every step with the number of steps taken so far (the reference's cosine / warm-up schedules,
+    experiments/train.py:216-286, are such functions of the epoch)."""
+
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, decoupled_weight_decay: bool = False, use_graph: bool = True,
                  autocast_dtype: Optional[torch.dtype] = None, process_group=None):
         self.model = model
-        self.lr, self.betas, self.eps = lr, betas, eps
-        self.weight_decay, self.decoupled = weight_decay, decoupled_weight_decay
+        self._hp = {"lr": float(lr), "betas": (float(betas[0]), float(betas[1])), "eps": float(eps),
+                    "weight_decay": float(weight_decay)}
+        self.decoupled = decoupled_weight_decay
+        self.lr_schedule = None
+        self._host_steps = 0
         self.autocast_dtype = autocast_dtype
         self.group = process_group
         self.world = world_size(process_group)
@@ -35,15 +59,61 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
+        self.hyper = torch.zeros(5, device=dev, dtype=torch.float32)
+        self._push_hyper()
+        self.param_groups = [_ParamGroup(self, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay,
+                                         params=self.params)]
         self.fp.broadcast(model.buffers(), src=0, group=self.group)
         self.use_graph = use_graph
         self._graph = None
         self._static = None
+        # modules that redraw their random features every k-th training forward (favor_plus.py:168-171): the decision is a
+        # host-side counter and the draw uses the host RNG + QR, neither of which can live inside a captured step
+        self._redraw = [m for m in model.modules() if getattr(m, "feature_redraw_interval", None) is not None]
+
+    # ---- hyper-parameters -------------------------------------------------------------------------------
+    lr = property(lambda self: self._hp["lr"], lambda self, v: self._set_hyper(lr=v))
+    betas = property(lambda self: self._hp["betas"], lambda self, v: self._set_hyper(betas=v))
+    eps = property(lambda self: self._hp["eps"], lambda self, v: self._set_hyper(eps=v))
+    weight_decay = property(lambda self: self._hp["weight_decay"], lambda self, v: self._set_hyper(weight_decay=v))
+
+    def set_lr(self, lr: float):
+        self._set_hyper(lr=lr)
+
+    def _set_hyper(self, **kw):
+        for k, v in kw.items():
+            self._hp[k] = (float(v[0]), float(v[1])) if k == "betas" else float(v)
+            if hasattr(self, "param_groups"):
+                dict.__setitem__(self.param_groups[0], k, self._hp[k])
+        if hasattr(self, "hyper"):
+            self._push_hyper()
+
+    def _push_hyper(self):
+        h = self._hp
+        self.hyper.copy_(torch.tensor([h["lr"], h["betas"][0], h["betas"][1], h["eps"], h["weight_decay"]],
+                                      dtype=torch.float32), non_blocking=False)
+
+    def _before_step(self):
+        """Host-side work that must not be recorded: the LR schedule and the feature redraw (done here with a host counter,
+        rank 0's draw broadcast to every replica, the module's own counter-driven redraw switched off)."""
+        if self.lr_schedule is not None:
+            self._set_hyper(lr=self.lr_schedule(self._host_steps))
+        for m in self._redraw:
+            if self._host_steps % m.feature_redraw_interval == 0:
+                m._create_random_features()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.broadcast(m.omega, src=0, group=self.group)
+            m.redraw_counter += 1
+        self._host_steps += 1
 
     # ---- one optimisation step on device-resident inputs -------------------------------------------------
     def _step_impl(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.gflat.zero_()
         prev, ops.GRAD_INPLACE = ops.GRAD_INPLACE, True  # fused kernels add straight into the flat gradient buffer
+        held = [(m, m.feature_redraw_interval) for m in self._redraw]
+        for m, _ in held:
+            m.feature_redraw_interval = None  # _before_step() owns the redraw; the module must not sync / redraw in here
         try:
             if self.autocast_dtype is not None:
                 with torch.autocast("cuda", dtype=self.autocast_dtype):
@@ -58,12 +128,13 @@ class Trainer:
             loss.backward()
         finally:
             ops.GRAD_INPLACE = prev
+            for m, k in held:
+                m.feature_redraw_interval = k
         self.fp.allreduce_grad(self.group)
         self.step_count += 1
-        C.check(C.load().erv_adam_step(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
-                                       self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                       self.weight_decay, int(self.decoupled), 1.0 / self.world, 0,
-                                       C.ptr(self.step_count), C.stream()), "adam_step")
+        C.check(C.load().erv_adam_step_dev(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg),
+                                           C.ptr(self.exp_avg_sq), self.flat.numel(), C.ptr(self.hyper), int(self.decoupled),
+                                           1.0 / self.world, C.ptr(self.step_count), C.stream()), "adam_step")
         return loss.detach()
 
     def _capture(self, images: torch.Tensor, labels: torch.Tensor):
@@ -73,11 +144,12 @@ class Trainer:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream: allocator, cuBLAS handles, lazy kernel loads
-            keep = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)]
+            state = [self.flat, self.exp_avg, self.exp_avg_sq, self.step_count, *self.model.buffers()]
+            keep = [t.clone() for t in state]
             for _ in range(3):
                 self._step_impl(*self._static)
-            for dst, src in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), keep):
-                dst.copy_(src)  # the warm-up steps must not train: the first replay is optimisation step 1
+            for dst, src in zip(state, keep):
+                dst.copy_(src)  # the warm-up steps must not train (nor move any buffer): the first replay is step 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
@@ -89,6 +161,7 @@ class Trainer:
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """images/labels may be CUDA tensors or pinned host tensors (copied asynchronously).  Returns the loss as
         a device tensor (no host sync)."""
+        self._before_step()
         if not self.use_graph:
             return self._step_impl(images.to(self.flat.device, non_blocking=True),
                                    labels.to(self.flat.device, non_blocking=True))
@@ -127,6 +200,7 @@ class Trainer:
         assert hasattr(self, "_stage") and self._stage_get < self._stage_put, "call prefetch() first"
         slot = self._stage_get % 2
         self._stage_get += 1
+        self._before_step()
         cur = torch.cuda.current_stream()
         cur.wait_event(self._stage_events[slot])
         img, lab = self._stage[slot]
@@ -167,9 +241,11 @@ class Trainer:
         g = groups[0]
         if g.get("amsgrad", False) or g.get("maximize", False):
             raise ValueError("amsgrad / maximize are not supported by the fused flat Adam step")
-        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
-        self.weight_decay = float(g.get("weight_decay", 0.0))
-        self.decoupled = bool(g.get("decoupled_weight_decay", self.decoupled))
+        self._set_hyper(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g.get("weight_decay", 0.0))
+        decoupled = bool(g.get("decoupled_weight_decay", self.decoupled))
+        if decoupled != self.decoupled:  # the only hyper-parameter still recorded by value
+            self._graph = None
+        self.decoupled = decoupled
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         steps = set()
@@ -186,8 +262,7 @@ class Trainer:
         if len(steps) != 1:
             raise ValueError(f"parameters are at different step counts {sorted(steps)}; the flat step keeps one counter")
         self.step_count.fill_(steps.pop())
-        if self._graph is not None:  # hyper-parameters are baked into a recorded step
-            self._graph = None
+        self._host_steps = int(self.step_count)
 
     def kernels_per_step(self) -> Optional[int]:
         """erv kernels launched per step in graph mode (counted while the graph was recorded)."""

@@ -1,8 +1,10 @@
 """The caller of the hot path: a small pre-norm ViT with injected attention / RPE plugins.
 
 Behaviourally equal to the reference's models/core/base_vit.py and models/components/unified_transformer.py
-(same module names -> same state_dict keys, same init laws), so reference checkpoints load.  Everything
-here is stock torch (Linear / LayerNorm / GELU run on cuBLAS / ATen); only `block.attention` is ours.
+(same module names -> same state_dict keys, same init laws), so reference checkpoints load.  At the reference's
+dims (dim 32, MLP 64) the block around the attention core, the patch embedding (4x4 patches) and the head + loss run as
+fused kernels of this library (`_forward_fused`, `_fused_ends`); other geometries fall back to the op-by-op modules
+(Linear / LayerNorm / GELU on cuBLAS / ATen) around `block.attention`, which is always ours.
 """
 from typing import Callable, Dict, Optional
 
@@ -48,7 +50,8 @@ class UnifiedTransformerBlock(nn.Module):
             return False
         if att.qkv.weight.dtype != torch.float32 or att.proj.bias is None or not ops.block_supported(self.dim, self.mlp_dim):
             return False
-        return att.proj_dropout.p == self.mlp[2].p == self.mlp[4].p
+        # p >= 1 (nn.Dropout accepts 1.0: everything dropped) has no finite 1/(1-p): leave it to the op-by-op modules
+        return att.proj_dropout.p == self.mlp[2].p == self.mlp[4].p and att.proj_dropout.p < 1.0
 
     def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
         att = self.attention

@@ -228,6 +228,11 @@ int erv_toeplitz_matmul_bwd(const float* c, const float* x, const float* dy, flo
 int erv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
                   float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
+/* The same step with the hyper-parameters read from device memory at run time: hyper = [lr, beta1, beta2, eps,
+ * weight_decay] (5 floats) and the step counter *step_dev.  A CUDA graph that recorded this call follows a learning-rate
+ * schedule (experiments/train.py:216-286 create_lr_scheduler) by rewriting hyper[0] between replays. */
+int erv_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* hyper,
+                      int decoupled_wd, float grad_scale, const int64_t* step_dev, void* stream);
 
 /* ---- the rest of the block, for the reference's small model dims ------------- */
 

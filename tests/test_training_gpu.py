@@ -105,3 +105,64 @@ def test_feature_redraw_interval_on_device():
     att.eval()
     att(x)
     assert int(att.redraw_counter) == 4 and torch.equal(att.omega, seen[-1])
+
+
+def test_learning_rate_change_after_capture_is_honoured():
+    """hyper-parameters used to be baked into the captured graph.  They now live in device memory: changing the
+    learning rate after the first (captured) step, through param_groups, set_lr or a schedule, matches torch.optim.Adam."""
+    from erv_b200.train import Trainer
+    batches = _batches(6)
+    ref = _model()
+    ours = copy.deepcopy(ref)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    _torch_adam_steps(ref, opt, batches[:2])
+    for g in opt.param_groups:
+        g["lr"] = 1e-2
+    _torch_adam_steps(ref, opt, batches[2:4])
+    for g in opt.param_groups:
+        g["lr"] = 5e-4
+    _torch_adam_steps(ref, opt, batches[4:])
+    tr = Trainer(ours, lr=1e-3, use_graph=True)
+    for b in batches[:2]:
+        tr.step(*b)
+    assert tr._graph is not None
+    graph = tr._graph
+    for g in tr.param_groups:
+        g["lr"] = 1e-2
+    assert tr.lr == 1e-2
+    for b in batches[2:4]:
+        tr.step(*b)
+    tr.set_lr(5e-4)
+    for b in batches[4:]:
+        tr.step(*b)
+    assert tr._graph is graph  # no re-capture was needed
+    for (k, a), (_, b) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert rel_l2(b, a) < 3e-4, k
+    # a schedule callable
+    tr2 = Trainer(_model(), lr=1.0, use_graph=True)
+    tr2.lr_schedule = lambda step: 1e-3 * (step + 1)
+    for b in batches[:3]:
+        tr2.step(*b)
+    assert abs(tr2.lr - 3e-3) < 1e-12 and abs(float(tr2.hyper[0]) - 3e-3) < 1e-9
+
+
+def test_feature_redraw_runs_outside_the_captured_step():
+    """feature_redraw_interval used to sync (int(redraw_counter)) and redraw inside stream capture.  The Trainer
+    now redraws on the host before the replay; the warm-up passes of the capture leave omega and the counter untouched."""
+    from erv_b200 import MNIST_CONFIG, create_model
+    from erv_b200.train import Trainer
+    torch.manual_seed(0)
+    model = create_model("performer_favor", MNIST_CONFIG, dropout=0.0,
+                         attention_config={"feature_redraw_interval": 2}).to("cuda").train()
+    attn = model.transformer_blocks[0].attention
+    assert attn.feature_redraw_interval == 2
+    tr = Trainer(model, lr=1e-3, use_graph=True)
+    seen = []
+    for i, b in enumerate(_batches(5)):
+        loss = tr.step(*b)
+        assert torch.isfinite(loss)
+        seen.append(attn.omega.clone())
+        assert int(attn.redraw_counter) == i + 1
+    assert attn.feature_redraw_interval == 2
+    assert torch.equal(seen[0], seen[1]) and torch.equal(seen[2], seen[3])  # steps 0, 2, 4 redraw
+    assert not torch.equal(seen[1], seen[2]) and not torch.equal(seen[3], seen[4])
