@@ -19,6 +19,13 @@ int la_grid(int B, int H);
 int la_slots(int B, int H);
 size_t wt_bytes(int H, int DH, int M);
 int prep_wt_public(const float* omega, float* wt, int H, int DH, int M, int kind, cudaStream_t st);
+// tcgen05 KERPLE tiles (erv_ktile_tc.cu)
+bool ktile_tc_eligible(int N, int DH, int M);
+int ktile_tc_forward(const void* qkv, void* out, float* den, const float* wt, const float* cexp, int B, int N, int H, int DH,
+                     int M, int kind, int dtype, cudaStream_t st);
+int ktile_tc_backward(const void* qkv, const void* out, const float* den, const void* dout, void* dqkv, float* dbias,
+                      float* dbias_part, const float* wt, const float* cexp, int B, int N, int H, int DH, int M, int kind,
+                      int dtype, cudaStream_t st);
 
 constexpr int TQ = 64;        // tile rows / cols
 constexpr int LDP = TQ + 4;   // stride of the 64x64 weight tiles (16-byte aligned rows)
@@ -887,13 +894,21 @@ extern "C" size_t erv_kerple_attention_workspace(int B, int N, int H, int head_d
   return kerple_ws(B, N, H, head_dim, M, backward).total;
 }
 
-static int kerple_features(const void* qkv, char* ws, const KerpleWs& w, const float* omega, const float* bias, int B,
-                           int N, int H, int DH, int M, int kind, int dtype, cudaStream_t st) {
+// W^T rows and exp(bias) into the workspace
+static int kerple_tables(char* ws, const KerpleWs& w, const float* omega, const float* bias, int N, int H, int DH, int M,
+                         int kind, cudaStream_t st) {
   int rc = prep_wt_public(omega, (float*)(ws + w.wt), H, DH, M, kind, st);
   if (rc) return rc;
   size_t nb = (size_t)H * (2 * N - 1);
   exp_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(bias, (float*)(ws + w.cexp), nb);
   ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}
+
+static int kerple_features(const void* qkv, char* ws, const KerpleWs& w, const float* omega, const float* bias, int B,
+                           int N, int H, int DH, int M, int kind, int dtype, cudaStream_t st) {
+  int rc = kerple_tables(ws, w, omega, bias, N, H, DH, M, kind, st);
+  if (rc) return rc;
   const int ld = (int)kerple_ldphi(M);
   const size_t es = dtype == ERV_F32 ? 4 : 2;
   const size_t plane = (size_t)B * H * N * ld;
@@ -919,6 +934,12 @@ extern "C" int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_o
   if (workspace_bytes < w.total) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
+  if (ktile_tc_eligible(N, head_dim, M)) {  // tensor-core tiles: features computed in the tile, nothing staged in HBM
+    rc = kerple_tables(ws, w, omega, rel_pos_bias, N, H, head_dim, M, kind, st);
+    if (rc) return rc;
+    return ktile_tc_forward(qkv, out, den_out, (const float*)(ws + w.wt), (const float*)(ws + w.cexp), B, N, H, head_dim, M,
+                            kind, dtype, st);
+  }
   rc = kerple_features(qkv, ws, w, omega, rel_pos_bias, B, N, H, head_dim, M, kind, dtype, st);
   if (rc) return rc;
   const int ld = (int)kerple_ldphi(M);
@@ -944,6 +965,13 @@ extern "C" int erv_kerple_attention_bwd(const void* qkv, const void* out, const 
   if (workspace_bytes < w.total) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
+  static const bool tc_bwd_off = getenv("ERV_DISABLE_KTILE_TC_BWD") != nullptr;
+  if (ktile_tc_eligible(N, head_dim, M) && !tc_bwd_off) {
+    rc = kerple_tables(ws, w, omega, rel_pos_bias, N, H, head_dim, M, kind, st);
+    if (rc) return rc;
+    return ktile_tc_backward(qkv, out, den, dout, dqkv, dbias, (float*)(ws + w.dpart), (const float*)(ws + w.wt),
+                             (const float*)(ws + w.cexp), B, N, H, head_dim, M, kind, dtype, st);
+  }
   rc = kerple_features(qkv, ws, w, omega, rel_pos_bias, B, N, H, head_dim, M, kind, dtype, st);
   if (rc) return rc;
   const int ld = (int)kerple_ldphi(M);
