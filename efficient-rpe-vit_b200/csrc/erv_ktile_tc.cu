@@ -19,7 +19,7 @@
 //     floor(128 / N) (batch, head) pairs per tile and mask the cross-pair blocks; long sequences walk 128-token tiles.
 //   * 512 threads = 4 per tile row: thread (row, quarter) owns 32 of the 128 columns of a score tile (16 of the 64 features).
 #include "erv_feat.cuh"
-#include "erv_tc_common.cuh"
+#include "erv_tile_tc.cuh"
 
 namespace erv {
 
@@ -39,14 +39,9 @@ struct KtArgs {
   FeatGeom g;
 };
 
-constexpr int KT = 128;              // tile rows
 constexpr int KMP = 64;              // padded feature count of this path
-constexpr int KTHREADS = 512;
 constexpr uint32_t KI_SBO = (KMP / 8) * 128;  // K-major [128 x 64] bf16 image: 8-row groups 1024 B apart, k-chunks 128 B apart
 constexpr uint32_t KI_BYTES = 16 * KI_SBO;    // 16 KB per level
-constexpr uint32_t VI_CH = 16 * 128;          // MN-major [K = 128 tokens][N] image: 8-column chunks 2048 B apart
-constexpr uint32_t XD_SBO = 256;              // K-major [128 x 16] bf16 image (dO, v): 8-row groups 256 B apart
-constexpr uint32_t XD_BYTES = 16 * XD_SBO;    // 4 KB per level
 
 // ---- shared-memory plan (bytes) -----------------------------------------------------------------------------
 struct KtPlan {
@@ -183,30 +178,6 @@ __device__ __forceinline__ void kt_features(KtCtx& c, const T* __restrict__ base
     for (int e = 0; e < 8; ++e) v[e] = pv[8 * cc + e];
     store_split8(dst, dst + KI_BYTES, (uint32_t)(c.row >> 3) * KI_SBO + (uint32_t)(2 * c.quarter + cc) * 128 + (c.row & 7) * 16, v);
   }
-}
-
-// one token row (registers) -> K-major bf16 hi/lo image [128 x 16]
-__device__ __forceinline__ void kt_store_row_kmajor(uint8_t* img, int row, const float (&x)[16]) {
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = x[8 * cc + e];
-    store_split8(img, img + XD_BYTES, (uint32_t)(row >> 3) * XD_SBO + (uint32_t)cc * 128 + (row & 7) * 16, v);
-  }
-}
-// one token row -> MN-major image [K = token][N = 48]: chunks 0,1 hi | 2 = [extra,0..] | 3 = 0 | 4,5 lo
-__device__ __forceinline__ void kt_store_row_mnmajor(uint8_t* img, int row, const float (&x)[16], float extra) {
-  const uint32_t off = (uint32_t)(row >> 3) * 128 + (row & 7) * 16;
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = x[8 * cc + e];
-    store_split8(img + (uint32_t)cc * VI_CH, img + (uint32_t)(4 + cc) * VI_CH, off, v);
-  }
-  *reinterpret_cast<uint4*>(img + 2 * VI_CH + off) = make_uint4((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(extra)), 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(img + 3 * VI_CH + off) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Toeplitz coefficients of a tile pair into shared memory: packed tiles index the whole table with (j_n - i_n) + N - 1,
@@ -730,7 +701,7 @@ static void kt_fill(KtArgs& a, int B, int N, int H, int M, int kind) {
   a.nqt = (N + KT - 1) / KT;
 }
 
-int ktile_tc_grid_x(int B, int N) { return N <= KT ? (B + KT / N - 1) / (KT / N) : B * ((N + KT - 1) / KT); }
+int ktile_tc_grid_x(int B, int N) { return tile_tc_grid_x(B, N); }
 
 int ktile_tc_forward(const void* qkv, void* out, float* den, const float* wt, const float* cexp, int B, int N, int H, int DH,
                      int M, int kind, int dtype, cudaStream_t st) {

@@ -99,6 +99,63 @@ __device__ __forceinline__ void prologue_row(float (&x)[DH], int rot, const floa
   for (int a = 0; a < DH; ++a) x[a] *= prescale;
 }
 
+// inverse of the rotation for a gradient row dy: rotate back, and for the Circulant rotation accumulate this token's share of
+// dL/dg into the CTA-private slot.  Out of line for the same reason as rotate_row (erv_tc_common.cuh).
+template <typename T, int DH>
+__device__ __noinline__ void rotate_row_bwd(const float* __restrict__ dy, float* __restrict__ dxr, int rot,
+                                            const float* __restrict__ ta, const float* __restrict__ tb, int h, int n, int N,
+                                            float* dg_slot, const T* x_raw_row) {
+  if (rot == ERV_ROT_ROPE) {
+#pragma unroll
+    for (int m = 0; m < DH / 2; ++m) {
+      const float c = __ldg(ta + (size_t)n * (DH / 2) + m), s = __ldg(tb + (size_t)n * (DH / 2) + m);
+      dxr[2 * m] = dy[2 * m] * c + dy[2 * m + 1] * s;
+      dxr[2 * m + 1] = dy[2 * m + 1] * c - dy[2 * m] * s;
+    }
+  } else {
+    float g[DH], d[DH];
+    load_row<float, DH>(ta + ((size_t)h * N + n) * DH, g);
+#pragma unroll
+    for (int aa = 0; aa < DH; ++aa) d[aa] = dy[aa];
+#pragma unroll
+    for (int bq = 0; bq < DH; ++bq) {
+      float a = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < DH; ++aa) a = fmaf(g[(aa - bq) & (DH - 1)], d[aa], a);
+      dxr[bq] = a;
+    }
+    if (dg_slot != nullptr && n >= 1) {
+      float xr[DH];
+      load_row<T, DH>(x_raw_row, xr);
+#pragma unroll
+      for (int m = 0; m < DH; ++m) {
+        float a = 0.f;
+#pragma unroll
+        for (int aa = 0; aa < DH; ++aa) a = fmaf(d[aa], xr[(aa - m) & (DH - 1)], a);
+        dg_slot[(size_t)n * DH + m] += a;  // slot private to this (CTA, pair side), row private to this thread
+      }
+    }
+  }
+}
+
+// inverse of prologue_row for a gradient row dy (already multiplied by the Dh^-1/4 scale)
+template <typename T, int DH>
+__device__ __forceinline__ void prologue_row_bwd(const float (&dy)[DH], float (&dxr)[DH], int rot, const float* ta,
+                                                 const float* tb, int h, int n, int N, float* dg_slot,
+                                                 const T* x_raw_row) {
+  if (rot == ERV_ROT_ROPE || rot == ERV_ROT_CIRCULANT) {
+    float tin[DH], tout[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) tin[d] = dy[d];
+    rotate_row_bwd<T, DH>(tin, tout, rot, ta, tb, h, n, N, dg_slot, x_raw_row);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dxr[d] = tout[d];
+  } else {
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dxr[d] = dy[d];
+  }
+}
+
 // write one token row as the hi / lo TF32 images of a K-major [128 x DH] operand
 template <int DH>
 __device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const float (&x)[DH], int t) {

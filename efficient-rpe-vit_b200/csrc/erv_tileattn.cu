@@ -19,6 +19,14 @@ int la_grid(int B, int H);
 int la_slots(int B, int H);
 size_t wt_bytes(int H, int DH, int M);
 int prep_wt_public(const float* omega, float* wt, int H, int DH, int M, int kind, cudaStream_t st);
+// tcgen05 softmax tiles (erv_stile_tc.cu)
+bool stile_tc_eligible(int N, int DH);
+int stile_tc_forward(const void* qkv, void* out, float* lse, float* attn_out, const uint8_t* mask, int B, int N, int H, int rot,
+                     const float* ta, const float* tb, float dropout_p, uint64_t seed, const long long* seed_dev, int dtype,
+                     cudaStream_t st);
+int stile_tc_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, const uint8_t* mask,
+                      int B, int N, int H, int rot, const float* ta, const float* tb, float* dg_part, int slots,
+                      float dropout_p, uint64_t seed, const long long* seed_dev, int dtype, cudaStream_t st);
 // tcgen05 KERPLE tiles (erv_ktile_tc.cu)
 bool ktile_tc_eligible(int N, int DH, int M);
 int ktile_tc_forward(const void* qkv, void* out, float* den, const float* wt, const float* cexp, int B, int N, int H, int DH,
@@ -822,6 +830,8 @@ extern "C" int erv_softmax_attention_fwd(const void* qkv, void* out, float* lse_
     return ERV_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (stile_tc_eligible(N, head_dim))  // tensor-core tiles: rotation in the tile prologue, nothing staged in HBM
+    return stile_tc_forward(qkv, out, lse_out, attn_out, mask, B, N, H, rot, tab_a, tab_b, dropout_p, seed, seed_dev, dtype, st);
   RotPackArgs r{qkv, nullptr, (float*)workspace, nullptr, tab_a, tab_b, nullptr, B, N, H, rot, 1};
   rc = dtype == ERV_F32 ? rot_pack<float, false>(r, head_dim, st) : rot_pack<__nv_bfloat16, false>(r, head_dim, st);
   if (rc) return rc;
@@ -853,10 +863,16 @@ extern "C" int erv_softmax_attention_bwd(const void* qkv, const void* out, const
     return ERV_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int slots = la_slots(B, H);
+  static const bool stile_bwd_off = getenv("ERV_DISABLE_STILE_TC_BWD") != nullptr;
+  if (stile_tc_eligible(N, head_dim) && !stile_bwd_off) {
+    if (rot == ERV_ROT_CIRCULANT) ERV_CUDA(cudaMemsetAsync(dg_part, 0, (size_t)H * slots * N * head_dim * sizeof(float), st));
+    return stile_tc_backward(qkv, out, lse, dout, dqkv, mask, B, N, H, rot, tab_a, tab_b,
+                             rot == ERV_ROT_CIRCULANT ? dg_part : nullptr, slots, dropout_p, seed, seed_dev, dtype, st);
+  }
   const size_t plane = (size_t)B * H * N * head_dim;
   float* rows = (float*)workspace;
   float* drows = (float*)((char*)workspace + erv_softmax_attention_workspace(B, N, H, head_dim, rot, 0));
-  const int slots = la_slots(B, H);
   RotPackArgs r{qkv, dqkv, rows, drows, tab_a, tab_b, rot == ERV_ROT_CIRCULANT ? dg_part : nullptr, B, N, H, rot, slots};
   rc = dtype == ERV_F32 ? rot_pack<float, false>(r, head_dim, st) : rot_pack<__nv_bfloat16, false>(r, head_dim, st);
   if (rc) return rc;
