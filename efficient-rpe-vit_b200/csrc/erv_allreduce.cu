@@ -1,0 +1,97 @@
+// One-shot sum all-reduce of the flat gradient over peer memory (NVLink 5 / NVSwitch), for the data-parallel step of
+// erv_b200.train (one all-reduce of 28-57 k floats per step).
+//
+// At this size (~230 KB) an NCCL all-reduce is pure latency (ring / tree steps, several kernel phases): it cost 0.15 ms of
+// a 1.75 ms step on 8 GPUs in round 1.  Here every rank's gradient buffer lives in symmetric memory (one allocation per
+// rank, every peer mapped into every process by torch.distributed._symmetric_memory); ONE single-CTA kernel per rank
+//   1. publishes "my gradient is complete" into every peer's flag word and waits for all peers,
+//   2. reads all `world` buffers through NVLink and adds them IN RANK ORDER (every rank computes bit-identical sums, so the
+//      replicas stay identical), writing the result to a local output buffer,
+//   3. publishes "I have finished reading" and waits for all peers, so the next step may overwrite the buffers.
+// Flags carry a monotonically increasing epoch (no resets); waits are bounded and trap instead of hanging the GPU.
+// Every rank must launch this kernel the same number of times.
+#include "erv_common.cuh"
+
+namespace erv {
+
+constexpr int kArMaxWorld = 8;
+
+struct ArArgs {
+  const float* peer[kArMaxWorld];  // every rank's symmetric buffer as mapped in this process
+  uint32_t* flags[kArMaxWorld];    // every rank's flag block: [2][kArMaxWorld] words
+  float* out;
+  uint32_t* epoch;                 // this rank's launch counter (device memory)
+  int n4, rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {  // bypasses the (non-coherent) L1 for peer data
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void ar_barrier(const ArArgs& a, int phase, uint32_t ep) {
+  const int t = threadIdx.x;
+  if (t < a.world) {
+    __threadfence_system();
+    st_release_sys(a.flags[t] + phase * kArMaxWorld + a.rank, ep);  // slot `rank` of peer t
+    const uint32_t* mine = a.flags[a.rank] + phase * kArMaxWorld + t;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(mine) - ep) < 0) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a peer never arrived
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(const ArArgs a) {
+  __shared__ uint32_t ep_s;
+  if (threadIdx.x == 0) ep_s = *a.epoch + 1;
+  __syncthreads();
+  const uint32_t ep = ep_s;
+  ar_barrier(a, 0, ep);
+  for (int i = threadIdx.x; i < a.n4; i += blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kArMaxWorld; ++r)
+      if (r < a.world) {
+        const float4 v = ld_peer4(a.peer[r] + 4 * (size_t)i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    reinterpret_cast<float4*>(a.out)[i] = s;
+  }
+  __syncthreads();
+  ar_barrier(a, 1, ep);
+  if (threadIdx.x == 0) *a.epoch = ep;
+}
+
+}  // namespace erv
+
+using namespace erv;
+
+extern "C" int erv_allreduce_oneshot(const void* const* peer_bufs, size_t n, size_t flag_offset_floats, float* out, int rank,
+                                     int world, uint32_t* epoch_dev, void* stream) {
+  ERV_CHECK_ARG(peer_bufs && out && epoch_dev, "erv_allreduce_oneshot: null pointer");
+  ERV_CHECK_ARG(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, "erv_allreduce_oneshot: rank %d / world %d",
+                rank, world);
+  ERV_CHECK_ARG(n % 4 == 0 && flag_offset_floats >= n && flag_offset_floats % 4 == 0,
+                "erv_allreduce_oneshot: n and the flag offset must be multiples of 4 floats, flags behind the data");
+  ArArgs a{};
+  for (int r = 0; r < world; ++r) {
+    ERV_CHECK_ARG(peer_bufs[r] != nullptr, "erv_allreduce_oneshot: peer %d not mapped", r);
+    a.peer[r] = static_cast<const float*>(peer_bufs[r]);
+    a.flags[r] = reinterpret_cast<uint32_t*>(const_cast<float*>(a.peer[r]) + flag_offset_floats);
+  }
+  a.out = out; a.epoch = epoch_dev; a.n4 = (int)(n / 4); a.rank = rank; a.world = world;
+  allreduce_oneshot_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  ERV_LAUNCH_CHECK();
+  return ERV_OK;
+}

@@ -62,3 +62,55 @@ class FlatParams:
         """Sum over ranks, in place; the 1/world factor is folded into the optimizer step."""
         if world_size(group) > 1:
             dist.all_reduce(self.grad, group=group)
+
+
+class BucketedReducer:
+    """Backward + gradient all-reduce in two buckets, the first one under the rest of the backward.
+
+    The flat gradient is split where `model.transformer_blocks[1]` starts.  Everything from there on (blocks 1.., final norm,
+    head) has its gradient after the first part of the backward; its all-reduce is launched asynchronously (on the process
+    group's own stream, forked from the step's stream) and runs under the backward of block 0 and the patch embedding; the
+    second bucket (class token, positions, embedding, block 0) follows.  Both are called from the thread that runs the step,
+    so they are recorded when the step is captured in a CUDA graph.  The backward is cut at the output of block 0, which the
+    model records as `model._cut_tensor` when `model._cut_after == 0` (erv_b200.vit.BaseViT.features).
+
+    Measured on 2 B200 (gpurun_out/r2_dp_*_n2.json): the split costs more than it hides at the reference dims (1.674 ms per
+    step against 1.587 with one all-reduce: two latency-bound NCCL calls instead of one, and the cut adds an autograd pass), so
+    it is opt-in (ERV_BUCKET_ALLREDUCE=1).  Otherwise, and when there is nothing to overlap (one rank, fewer than two blocks,
+    a parameter order that does not follow the module order): `loss.backward()` + one all-reduce."""
+
+    def __init__(self, model: torch.nn.Module, fp: FlatParams, group=None):
+        import os
+        self.model, self.fp, self.group = model, fp, group
+        self.split = None
+        blocks = getattr(model, "transformer_blocks", None)
+        if world_size(group) == 1 or blocks is None or len(blocks) < 2 or not os.environ.get("ERV_BUCKET_ALLREDUCE"):
+            return
+        first = next(iter(blocks[1].parameters()), None)
+        idx = next((i for i, q in enumerate(fp.params) if q is first), None) if first is not None else None
+        if not idx:
+            return
+        late = {id(q) for b in list(blocks)[1:] for q in b.parameters()}
+        head = getattr(model, "mlp_head", None)
+        if head is not None:
+            late |= {id(q) for q in head.parameters()}
+        if any(id(q) not in late for q in fp.params[idx:]) or any(id(q) in late for q in fp.params[:idx]):
+            return
+        self.split = (idx, fp.offsets[idx])
+        model._cut_after = 0
+
+    def backward_and_reduce(self, loss: torch.Tensor):
+        cut = getattr(self.model, "_cut_tensor", None)
+        if self.split is None or cut is None:
+            loss.backward()
+            self.fp.allreduce_grad(self.group)
+            return
+        idx, off = self.split
+        self.model._cut_tensor = None
+        cut.retain_grad()
+        torch.autograd.backward(loss, inputs=[*self.fp.params[idx:], cut], retain_graph=True)
+        work = dist.all_reduce(self.fp.grad[off:], group=self.group, async_op=True)
+        torch.autograd.backward(cut, grad_tensors=cut.grad, inputs=self.fp.params[:idx])
+        cut.grad = None
+        work.wait()
+        dist.all_reduce(self.fp.grad[:off], group=self.group)

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from . import _capi as C
 from . import ops
-from .parallel import FlatParams, world_size
+from .parallel import BucketedReducer, FlatParams, world_size
 
 
 class _ParamGroup(dict):
@@ -70,6 +70,7 @@ class Trainer:
         # modules that redraw their random features every k-th training forward (favor_plus.py:168-171): the decision is a
         # host-side counter and the draw uses the host RNG + QR, neither of which can live inside a captured step
         self._redraw = [m for m in model.modules() if getattr(m, "feature_redraw_interval", None) is not None]
+        self.reducer = BucketedReducer(model, self.fp, self.group)
 
     # ---- hyper-parameters -------------------------------------------------------------------------------
     lr = property(lambda self: self._hp["lr"], lambda self, v: self._set_hyper(lr=v))
@@ -125,12 +126,11 @@ class Trainer:
                 loss = self.model.loss(images, labels)  # head + criterion fused when the model supports it
             else:
                 loss = F.cross_entropy(self.model(images).float(), labels)
-            loss.backward()
+            self.reducer.backward_and_reduce(loss)
         finally:
             ops.GRAD_INPLACE = prev
             for m, k in held:
                 m.feature_redraw_interval = k
-        self.fp.allreduce_grad(self.group)
         self.step_count += 1
         C.check(C.load().erv_adam_step_dev(C.ptr(self.flat), C.ptr(self.gflat), C.ptr(self.exp_avg),
                                            C.ptr(self.exp_avg_sq), self.flat.numel(), C.ptr(self.hyper), int(self.decoupled),

@@ -140,8 +140,11 @@ class BaseViT(nn.Module):
         else:
             x = self.patch_embedding(self.patchify(x))
             x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding
-        for block in self.transformer_blocks:
+        cut = getattr(self, "_cut_after", None)
+        for i, block in enumerate(self.transformer_blocks):
             x = block(x)
+            if cut == i and x.requires_grad:  # erv_b200.train: the backward is split here to overlap the gradient all-reduce
+                self._cut_tensor = x
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -254,6 +254,16 @@ int erv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
                       float* dx, float* dgamma, float* dbeta, int R, int C, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ---- data-parallel gradient reduction --------------------------------- */
+
+/* One-shot sum all-reduce over peer memory: peer_bufs (HOST array of `world` device pointers) are every rank's symmetric
+ * buffer as mapped in this process (torch.distributed._symmetric_memory); each holds n floats of data and, at
+ * flag_offset_floats, 2 x 8 flag words that start at zero.  out (local, n floats) receives the sum, added in rank order.
+ * epoch_dev: one device uint32 per rank, starts at zero.  Every rank must make the same sequence of calls.  Replaces the
+ * NCCL all-reduce of the flat gradient (experiments/utils/training.py has no multi-GPU path). */
+int erv_allreduce_oneshot(const void* const* peer_bufs, size_t n, size_t flag_offset_floats, float* out, int rank,
+                          int world, uint32_t* epoch_dev, void* stream);
+
 /* ---- diagnostics -------------------------------------------------------------------------- */
 
 /* D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (TF32 or BF16 operands, fp32 accumulate in TMEM) using the shared-

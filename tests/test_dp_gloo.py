@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from erv_b200.parallel import FlatParams, shard_slice
+from erv_b200.parallel import BucketedReducer, FlatParams, shard_slice
 
 
 def _free_port():
@@ -74,3 +74,58 @@ def test_flat_params_are_views_and_shards_validate():
     assert m[0].weight.grad.abs().sum() == 0
     with pytest.raises(ValueError):
         shard_slice(10, 0, 4)
+
+
+class _TinyViT(torch.nn.Module):
+    """Parameter order and cut point of erv_b200.vit.BaseViT: embedding, blocks, head."""
+
+    def __init__(self):
+        super().__init__()
+        self.pos = torch.nn.Parameter(torch.randn(1, 6) * 0.1)
+        self.patch_embedding = torch.nn.Linear(6, 6)
+        self.transformer_blocks = torch.nn.ModuleList(
+            [torch.nn.Sequential(torch.nn.LayerNorm(6), torch.nn.Linear(6, 6), torch.nn.GELU()) for _ in range(3)])
+        self.mlp_head = torch.nn.Sequential(torch.nn.LayerNorm(6), torch.nn.Linear(6, 3))
+
+    def forward(self, x):
+        x = self.patch_embedding(x) + self.pos
+        for i, b in enumerate(self.transformer_blocks):
+            x = x + b(x)
+            if getattr(self, "_cut_after", None) == i:
+                self._cut_tensor = x
+        return self.mlp_head(x)
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ERV_BUCKET_ALLREDUCE="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(5)
+        model = _TinyViT()
+        fp = FlatParams(model.parameters())
+        red = BucketedReducer(model, fp)
+        assert red.split is not None and 0 < red.split[1] < fp.numel()
+        g = torch.Generator().manual_seed(0)
+        x, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+        sl = shard_slice(8, rank, world)
+        for _ in range(2):  # twice: the cut tensor is re-recorded by every forward
+            fp.zero_grad()
+            red.backward_and_reduce(torch.nn.functional.cross_entropy(model(x[sl]), y[sl], reduction="sum"))
+        out[rank] = (fp.grad.clone(), red.split)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_bucket_backward_matches_single_process():
+    """The split backward + two all-reduces (first bucket launched before block 0's backward) give the full-batch gradient."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_bucket_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(5)
+    ref = _TinyViT()
+    fp = FlatParams(ref.parameters())
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+    torch.nn.functional.cross_entropy(ref(x), y, reduction="sum").backward()
+    for r in range(world):
+        assert torch.allclose(out[r][0], fp.grad, atol=1e-5), (out[r][0] - fp.grad).abs().max()
