@@ -440,6 +440,9 @@ bool la_tc2_eligible(int N, int DH, int M);  // two pairs per tile (erv_linattn_
 int la_tc2_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
                    const float* ta, const float* tb, int dtype, float* state, cudaStream_t st);
 int tc2_mp(int M);
+bool la_pipe_eligible(int N, int DH, int M);  // warp-specialised, pipelined forward (erv_linattn_pipe.cu)
+int la_pipe_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
+                    const float* ta, const float* tb, int dtype, float* state, cudaStream_t st);
 int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
                     int dtype, const float* state, cudaStream_t st);
@@ -470,6 +473,8 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   ERV_CHECK_ARG(!(bwd && rot == ERV_ROT_CIRCULANT) || dg_part, "%s: dg_part missing", fn);
   if (ws_bytes < wt_bytes(H, DH, M)) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (!bwd && la_pipe_eligible(N, DH, M))
+    return la_pipe_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, state, st);
   if (!bwd && la_tc2_eligible(N, DH, M))
     return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, state, st);
   if (!bwd && la_tc_eligible(N, DH, M))

@@ -18,6 +18,7 @@ struct LaTcArgs {
   int B, N, H, M, Mp16, kind, rot;
   float prescale, inv_sqrt_m;
   float* state;  // optional [B*H][DH+1][Mp]: the finished [S|z] of every pair, saved for the backward (short-sequence kernel)
+  long long* trace = nullptr;  // optional phase trace (erv_debug_set_trace, builds with -DERV_TRACE only)
 };
 
 template <int DH>
