@@ -443,6 +443,9 @@ int tc2_mp(int M);
 bool la_pipe_eligible(int N, int DH, int M);  // warp-specialised, pipelined forward (erv_linattn_pipe.cu)
 int la_pipe_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int M, int kind, int rot,
                     const float* ta, const float* tb, int dtype, float* state, cudaStream_t st);
+int la_pipe_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
+                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
+                     int dtype, const float* state, cudaStream_t st);
 int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
                     int dtype, const float* state, cudaStream_t st);
@@ -456,7 +459,9 @@ int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqk
 // Floats of the [S|z] state the forward saves for the backward (0: these shapes recompute S in the backward).
 extern "C" size_t erv_linear_attention_state_floats(int B, int N, int H, int head_dim, int M) {
   if (B <= 0 || H <= 0 || !erv::la_tc2_eligible(N, head_dim, M)) return 0;
-  return (size_t)B * H * (head_dim + 1) * erv::tc2_mp(M);
+  // the pipelined kernels also keep three per-token statistics (normaliser, exponent shifts of the query / key rows)
+  const size_t aux = erv::la_pipe_eligible(N, head_dim, M) ? (size_t)3 * B * N * H : 0;
+  return (size_t)B * H * (head_dim + 1) * erv::tc2_mp(M) + aux;
 }
 
 static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, void* dqkv, const float* omega, int B,
@@ -484,6 +489,9 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
     const int slots = la_slots(B, H);
     float* dgp = (rot == ERV_ROT_CIRCULANT) ? dg_part : nullptr;
     if (dgp) ERV_CUDA(cudaMemsetAsync(dgp, 0, (size_t)H * slots * N * DH * sizeof(float), st));
+    static const bool pipe_bwd_off = getenv("ERV_DISABLE_PIPE_BWD") != nullptr;
+    if (la_pipe_eligible(N, DH, M) && state != nullptr && !pipe_bwd_off)  // needs the statistics the pipelined forward saved
+      return la_pipe_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
     if (la_tc2_eligible(N, DH, M) && !tc2_bwd_off)
       return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
     return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
