@@ -332,6 +332,9 @@ def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
     # ---- roofline: dominant attention kernel, CUDA events around its launches (separate eager pass) --------
     ops.PROFILE = {}
     for i in range(6):  # every rank runs the pass (the step contains the gradient all-reduce)
+        # keep the GPU busy while the host enqueues the eager step, so that every timed kernel is already queued when its
+        # predecessor ends and the events bracket its execution only (not the launch latency of an idle stream)
+        torch.cuda._sleep(int(2.0e7))
         trainer._step_impl(*pool[i % pool_n])
     torch.cuda.synchronize()
     stats = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.PROFILE.items()}

@@ -64,6 +64,7 @@ SIGNATURES = {
     "erv_toeplitz_matmul_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "erv_adam_step": (c_int, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _I, _F, c_int64, _P, _P]),
     "erv_adam_step_dev": (c_int, [_P, _P, _P, _P, _Z, _P, _I, _F, _P, _P]),
+    "erv_allreduce_flag_floats": (c_int, []),
     "erv_allreduce_oneshot": (c_int, [_P, _Z, _Z, _P, _I, _I, _P, _P]),
     "erv_linear_wgrad_supported": (c_int, [_I, _I, _I]),
     "erv_linear_wgrad_workspace": (c_size_t, [_I, _I, _I]),

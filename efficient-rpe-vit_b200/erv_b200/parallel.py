@@ -27,7 +27,9 @@ class FlatParams:
 
     ALIGN = 4  # floats
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], grad_alloc=None):
+        """grad_alloc(total) -> zero-filled fp32 tensor of >= total elements that will hold the flat gradient (used to place
+        it in NVLink-mapped symmetric memory, PeerAllReduce); default: a plain device tensor."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -38,7 +40,8 @@ class FlatParams:
             self.offsets.append(total)
             total += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32) if grad_alloc is None else grad_alloc(total)[:total]
+        self.reduce_hook = None  # set by PeerAllReduce: replaces the NCCL all-reduce of allreduce_grad()
         for p, n, off in zip(self.params, self.sizes, self.offsets):
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)
@@ -61,7 +64,68 @@ class FlatParams:
     def allreduce_grad(self, group=None):
         """Sum over ranks, in place; the 1/world factor is folded into the optimizer step."""
         if world_size(group) > 1:
-            dist.all_reduce(self.grad, group=group)
+            if self.reduce_hook is not None:
+                self.reduce_hook()
+            else:
+                dist.all_reduce(self.grad, group=group)
+
+
+class PeerAllReduce:
+    """The flat gradient in NVLink-mapped symmetric memory + the one-shot sum kernel erv_allreduce_oneshot.
+
+    At 28-57 k floats the NCCL all-reduce is pure latency (0.15 ms of a 1.75 ms step on 8 GPUs in round 1).  Here every rank
+    allocates its gradient buffer with torch.distributed._symmetric_memory, every process maps every peer's buffer, and one
+    8-CTA kernel per rank waits for the peers' gradients, adds the `world` buffers in rank order over NVLink (bit-identical
+    sums on every rank) and leaves the result in the local gradient buffer.  CUDA-graph capturable (no host round trip; the
+    launch counter lives on the device).  Use: `peer = PeerAllReduce.create(group)`, `fp = FlatParams(params, peer.alloc)`,
+    `peer.attach(fp)`; create() returns None where the path does not apply (one rank, CPU tensors, more than 8 ranks,
+    symmetric memory unavailable, ERV_NCCL_ALLREDUCE=1), and FlatParams then all-reduces through torch.distributed."""
+
+    def __init__(self, group, device):
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf = self.hdl = self.n = None
+
+    @classmethod
+    def create(cls, group=None, device=None):
+        import os
+        if world_size(group) < 2 or world_size(group) > 8 or os.environ.get("ERV_NCCL_ALLREDUCE"):
+            return None
+        if device is None or torch.device(device).type != "cuda" or dist.get_backend(group) != "nccl":
+            return None
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+        except Exception:
+            return None
+        return cls(group if group is not None else dist.group.WORLD, torch.device(device))
+
+    def alloc(self, total: int) -> torch.Tensor:
+        import importlib
+        symm = importlib.import_module("torch.distributed._symmetric_memory")
+        from . import _capi as C
+        self.n = (total + 3) // 4 * 4
+        nflag = C.load().erv_allreduce_flag_floats()
+        self.buf = symm.empty(self.n + nflag, dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # every rank's flags are zero before anyone can signal
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        import ctypes
+        self.ptrs = (ctypes.c_void_p * self.world)(*[int(q) for q in self.hdl.buffer_ptrs])
+        self.scratch = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self.buf
+
+    def attach(self, fp: "FlatParams"):
+        if fp.grad.data_ptr() != self.buf.data_ptr():
+            raise ValueError("the flat gradient was not allocated by this PeerAllReduce")
+        fp.reduce_hook = self.allreduce
+
+    def allreduce(self):
+        from . import _capi as C
+        C.check(C.load().erv_allreduce_oneshot(self.ptrs, self.n, self.n, C.ptr(self.scratch), self.rank, self.world,
+                                               C.ptr(self.epoch), C.stream()), "allreduce_oneshot")
 
 
 class BucketedReducer:

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from . import _capi as C
 from . import ops
-from .parallel import BucketedReducer, FlatParams, world_size
+from .parallel import BucketedReducer, FlatParams, PeerAllReduce, world_size
 
 
 class _ParamGroup(dict):
@@ -53,7 +53,11 @@ class Trainer:
         self.group = process_group
         self.world = world_size(process_group)
         C.require_cuda(next(model.parameters()))
-        self.fp = FlatParams(model.parameters())
+        # data-parallel runs on NVLink: the flat gradient lives in symmetric memory and is summed by one peer-memory kernel
+        self.peer = PeerAllReduce.create(self.group, next(model.parameters()).device)
+        self.fp = FlatParams(model.parameters(), grad_alloc=self.peer.alloc if self.peer else None)
+        if self.peer:
+            self.peer.attach(self.fp)
         self.params, self.flat, self.gflat = self.fp.params, self.fp.flat, self.fp.grad
         dev = self.flat.device
         self.exp_avg = torch.zeros_like(self.flat)

@@ -258,10 +258,12 @@ int erv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 
 /* One-shot sum all-reduce over peer memory: peer_bufs (HOST array of `world` device pointers) are every rank's symmetric
  * buffer as mapped in this process (torch.distributed._symmetric_memory); each holds n floats of data and, at
- * flag_offset_floats, 2 x 8 flag words that start at zero.  out (local, n floats) receives the sum, added in rank order.
- * epoch_dev: one device uint32 per rank, starts at zero.  Every rank must make the same sequence of calls.  Replaces the
- * NCCL all-reduce of the flat gradient (experiments/utils/training.py has no multi-GPU path). */
-int erv_allreduce_oneshot(const void* const* peer_bufs, size_t n, size_t flag_offset_floats, float* out, int rank,
+ * flag_offset_floats, erv_allreduce_flag_floats() flag words that start at zero.  On return (stream order) the local buffer
+ * holds the sum over ranks, added in rank order (bit-identical on every rank); scratch is n floats of local memory.
+ * epoch_dev: one device uint32 per rank, starts at zero, owned by this call.  Every rank must make the same sequence of
+ * calls.  Replaces the NCCL all-reduce of the flat gradient (the reference has no multi-GPU path). */
+int erv_allreduce_flag_floats(void);
+int erv_allreduce_oneshot(const void* const* peer_bufs, size_t n, size_t flag_offset_floats, float* scratch, int rank,
                           int world, uint32_t* epoch_dev, void* stream);
 
 /* ---- diagnostics -------------------------------------------------------------------------- */
