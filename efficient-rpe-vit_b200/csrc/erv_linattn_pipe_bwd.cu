@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
   __shared__ __align__(16) float lone_a[2][2][DH + 4];  // [group parity][pair side]: a (16), a16
   __shared__ __align__(16) float lone_v[2][2][DH];
   __shared__ __align__(16) float lone_x[2][2][2][DH];  // [group parity][q|k][pair side]: prepared rows
+  __shared__ __align__(16) float lone_xs[2][4][DH];    // [lone warp][row]: prepared rows of the group being projected
   __shared__ __align__(16) float lone_dy[2][DH];
   __shared__ __align__(16) uint8_t lone_raw[2][2][10][64];  // [lone warp][group parity][qA kA qB kB vA vB dOA dOB OA OB]
+  __shared__ __align__(16) float lone_aux[2][2][8];  // [lone warp][group parity][shift qA kA qB kB | den A B]: staged statistics
   __shared__ float lone_red[2][2][DH + 4];             // [lone warp][pair side]: partial W^T reductions + row sum
   __shared__ float red_dv[16][DH];                     // per compute warp: dv partials of the lone key
 
@@ -294,6 +296,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
               cp_async16(&lone_raw[lw][buf][ri][ch * 16], src + ch * (16 / (int)sizeof(T)));
             }
           }
+          if (lane < 6) {  // exponent shifts of the lone query / key rows, normalisers of the lone queries
+            const int sp = lane < 4 ? lane >> 1 : lane - 4, b = 2 * (g / H) + sp;
+            const int j = lane < 4 ? 1 + (lane & 1) : 0;
+            if (b < B)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(&lone_aux[lw][buf][lane])),
+                           "l"(aux + ((size_t)b * H + h) * 3 * N + j * N + N - 1)
+                           : "memory");
+          }
         }
         cp_async_commit();
       };
@@ -302,35 +312,47 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
         const int b2 = g / H;
         cp_async_wait_all();
         __syncwarp();
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {  // r = 2 * pair side + (0: query, 1: key)
-          const int sp = r >> 1, which = r & 1, b = 2 * b2 + sp;
-          const bool ok = b < B;
+        if (lane < 4) {  // lane r prepares row r = 2 * pair side + (0: query, 1: key)
+          const int sp = lane >> 1, which = lane & 1;
           float x[DH];
 #pragma unroll
           for (int a = 0; a < DH; ++a) x[a] = 0.f;
-          float shift = INFINITY;
-          if (ok) {
-            load_row<T, DH>(reinterpret_cast<const T*>(&lone_raw[lw][buf][r][0]), x);
+          if (2 * b2 + sp < B) {
+            load_row<T, DH>(reinterpret_cast<const T*>(&lone_raw[lw][buf][lane][0]), x);
             prologue_row<DH>(x, p.rot, p.ta, p.tb, h, N - 1, N, p.prescale);
-            shift = __ldg(aux + ((size_t)b * H + h) * 3 * N + (1 + which) * N + N - 1);
           }
-          if (lw == 0 && lane < 4) st4(&lone_x[buf][which][sp][4 * lane], make_float4(x[4 * lane], x[4 * lane + 1], x[4 * lane + 2], x[4 * lane + 3]));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = HF * lw + lane + 32 * i;
-            float acc = 0.f;
+          for (int c = 0; c < DH / 4; ++c) {
+            const float4 v = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            st4(&lone_xs[lw][lane][4 * c], v);
+            if (lw == 0) st4(&lone_x[buf][which][sp][4 * c], v);
+          }
+        }
+        __syncwarp();
 #pragma unroll
-            for (int d = 0; d < DH; ++d) acc = fmaf(x[d], wreg[i][d], acc);
-            float v = FAVOR ? ex2_approx(fmaf(acc, kLog2e, -shift)) : fmaxf(acc, 0.f) * p.inv_sqrt_m;
+        for (int i = 0; i < 4; ++i) {  // one feature at a time: its W^T row against the four rows
+          const int f = HF * lw + lane + 32 * i;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float4 xv = ld4(&lone_xs[lw][r][4 * c]);
+              acc[r] = fmaf(xv.x, wreg[i][4 * c], acc[r]); acc[r] = fmaf(xv.y, wreg[i][4 * c + 1], acc[r]);
+              acc[r] = fmaf(xv.z, wreg[i][4 * c + 2], acc[r]); acc[r] = fmaf(xv.w, wreg[i][4 * c + 3], acc[r]);
+            }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const bool ok = 2 * b2 + (r >> 1) < B;
+            float v = FAVOR ? ex2_approx(fmaf(acc[r], kLog2e, -lone_aux[lw][buf][r])) : fmaxf(acc[r], 0.f) * p.inv_sqrt_m;
             if ((PADDED && f >= M) || !ok) v = 0.f;
-            lone_s[buf][which][sp][f] = v;
+            lone_s[buf][r & 1][r >> 1][f] = v;
           }
         }
         if (lw == 0) {  // a = dO / den, a16 = -(dO . O) / den of the lone queries; v of the lone keys
           const int sp = lane >> 4, d = lane & 15, b = 2 * b2 + sp;
           const bool ok = b < B;
-          const float den = ok ? __ldg(aux + ((size_t)b * H + h) * 3 * N + N - 1) : 1.f;
+          const float den = ok ? lone_aux[lw][buf][4 + sp] : 1.f;
           const float dO = ok ? to_f(reinterpret_cast<const T*>(&lone_raw[lw][buf][6 + sp][0])[d]) : 0.f;
           const float O = ok ? to_f(reinterpret_cast<const T*>(&lone_raw[lw][buf][8 + sp][0])[d]) : 0.f;
           float dot = dO * O;
@@ -346,20 +368,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
         const int b2 = g / H;
 #pragma unroll 1
         for (int sp = 0; sp < 2; ++sp) {
-          float v16[16];
-          float rs = 0.f;
+          float gv[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v16[j] = 0.f;
+          for (int i = 0; i < 4; ++i) gv[i] = lone_g[which][sp][HF * lw + lane + 32 * i];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float gv = lone_g[which][sp][HF * lw + lane + 32 * i];
-            rs += gv;
+          for (int c = 0; c < 2; ++c) {  // 8 columns at a time keeps the W^T rows in registers
+            float v8[8];
 #pragma unroll
-            for (int d = 0; d < DH; ++d) v16[d] = fmaf(gv, wreg[i][d], v16[d]);
+            for (int j = 0; j < 8; ++j) {
+              v8[j] = gv[0] * wreg[0][8 * c + j];
+#pragma unroll
+              for (int i = 1; i < 4; ++i) v8[j] = fmaf(gv[i], wreg[i][8 * c + j], v8[j]);
+            }
+            const float t = warp_sum8(v8);
+            if (!(lane & 3)) lone_red[lw][sp][8 * c + (lane >> 2)] = t;
           }
-          const float t = warp_sum16(v16);
-          rs = warp_sum(rs);
-          if (!(lane & 1)) lone_red[lw][sp][lane >> 1] = t;
+          const float rs = warp_sum((gv[0] + gv[1]) + (gv[2] + gv[3]));
           if (lane == 0) lone_red[lw][sp][DH] = rs;
         }
         lbar();
@@ -401,9 +425,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
         mbar_wait(&bars[F_S], par);  // G of the lone queries (written while the S image was built)
         TR(2);
         w_reduce(g, 0, par);
+        TR(5);
         mbar_wait(&bars[F_DS], par);  // G of the lone keys, dv partials (written by the dS epilogue)
         TR(3);
         w_reduce(g, 1, par);
+        TR(6);
         if (lw == 0) {
           const int sp = lane >> 4, d = lane & 15, bb = 2 * (g / H) + sp;
           if (bb < B) {
@@ -532,6 +558,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
       }
     };
 
+    // Rows and state a later phase of this thread reads from global memory are prefetched one unit ahead (into L1 for the
+    // 64-byte token rows, into L2 for the 17 strided state words), so that no register is held and the consuming phase
+    // does not sit behind the memory latency.
+    auto pf_l1 = [](const void* q) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(q)); };
+    auto pf_l2 = [](const void* q) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q)); };
+    auto prefetch_unit = [&](int u, int g, int gn, bool has_next) {
+      const int b = 2 * (g / H) + side, bn = 2 * (gn / H) + side;
+      const bool v = b < B && n < Nm, vn = has_next && bn < B && n < Nm;
+      if (u == 0) {
+        if (part == 0 && v) pf_l1(qkv + qkv_off(b, n, 1, h, N, H, DH));          // key row: x images after C1(Q0)
+      } else if (u == 1) {
+        if (part == 1 && v) pf_l1(qkv + qkv_off(b, n, 2, h, N, H, DH));          // value row: end of the Q sweep
+      } else if (u == 2) {
+        if (part == 0 && vn) pf_l1(qkv + qkv_off(bn, n, 0, h, N, H, DH));        // next group's query row
+        if (part == 2 && v) pf_l1(qkv + qkv_off(b, n, 0, h, N, H, DH));          // query row again: dq epilogue
+        if (has_next) {                                                          // next group's [S|z] rows
+          const int sp = part >> 1, f = (part & 1) * HF + row, bs = 2 * (gn / H) + sp;
+          if (bs < B) {
+            const float* src = p.state + ((size_t)bs * H + h) * (DH + 1) * Mp + f;
+            if ((lane & 7) == 0)  // one prefetch per 32-byte sector of the warp's 128-byte line
+#pragma unroll
+              for (int d = 0; d <= DH; ++d) pf_l2(src + (size_t)d * Mp);
+          }
+        }
+      } else {
+        if (part == 1 && vn) {                                                   // next group's dO / O rows
+          pf_l1(dout + out_off(bn, n, h, N, H, DH));
+          pf_l1(outp + out_off(bn, n, h, N, H, DH));
+        }
+        if (part == 2 && v) pf_l1(qkv + qkv_off(b, n, 1, h, N, H, DH));          // key row again: dk epilogue
+      }
+    };
+
     // ---- preamble: first group's query rows, [a|a16] rows, S image
     const int g0 = blockIdx.x;
     if (part == 0) stage_x_row(g0, 0);
@@ -554,6 +613,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
         const int isk = u >> 1, hb = u & 1;
+        prefetch_unit(u, g, gn, has_next);
         // ---- C1: one feature half: P (tensor memory) -> phi -> hi/lo bf16 images
         TR(10 * u + 0);
         wait(D_T1 + u, par);
@@ -594,7 +654,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
           warp_arrive(&bars[F_XK]);
           shift_k = load_shift(g, 1);
         } else if (u == 2) {
-          if (part == 0) {  // dq rows: dq' = G [W^T|1] of the Q sweep has completed
+          if (part == 2) {  // dq rows: dq' = G [W^T|1] of the Q sweep has completed
             wait(D_T4 + 0, par);
             wait(D_T4 + 1, par);
             fence_after_sync();
@@ -726,7 +786,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) la_pipe_bwd_kernel(const LaPi
             if (has_next) stage_a_row(gn);
           }
           warp_arrive(&bars[F_AVQ]);
-          if (part == 0) {
+          if (part == 2) {
             wait(D_T4 + 2, par);
             wait(D_T4 + 3, par);
             fence_after_sync();

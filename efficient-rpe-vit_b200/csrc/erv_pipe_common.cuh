@@ -76,6 +76,23 @@ __device__ __forceinline__ float warp_sum16(float (&v)[16]) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// sums of 8 per-lane values over the warp in 9 shuffles; afterwards lane l holds the total of value (l >> 2) & 7
+__device__ __forceinline__ float warp_sum8(float (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o / 4; ++i) {
+      const float send = up ? v[i] : v[i + o / 4];
+      const float keep = up ? v[i + o / 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+  return t + __shfl_xor_sync(0xffffffffu, t, 1);
+}
+
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
