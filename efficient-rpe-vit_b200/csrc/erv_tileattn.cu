@@ -17,6 +17,11 @@ int launch_feature_map(const void* x, void* dx, size_t sb, size_t sh, size_t sn,
                        float prescale, int dtype, bool bwd, cudaStream_t st);
 int la_grid(int B, int H);
 int la_slots(int B, int H);
+// FFT route of the KERPLE forward for long sequences (erv_kerple_fft.cu)
+bool kerple_fft_eligible(int N, int DH, int M);
+size_t kerple_fft_ws_bytes(int B, int N, int H, int DH, int M);
+int kerple_fft_forward(const void* qkv, void* out, float* den, const float* phi_q, const float* phi_k, int ld,
+                       const float* cexp, void* ws, int B, int N, int H, int DH, int M, int dtype, cudaStream_t st);
 size_t wt_bytes(int H, int DH, int M);
 int prep_wt_public(const float* omega, float* wt, int H, int DH, int M, int kind, cudaStream_t st);
 // tcgen05 softmax tiles (erv_stile_tc.cu)
@@ -892,7 +897,7 @@ extern "C" int erv_softmax_attention_bwd(const void* qkv, const void* out, const
 // ---- KERPLE -----------------------------------------------------------------------------------------
 // workspace: W^T | exp(bias) [H][2N-1] | phi_q, phi_k [B*H][N][ldphi] | (bwd) dphi_q, dphi_k | dbias partials
 static size_t kerple_ldphi(int M) { return (size_t)(M + 7) / 8 * 8; }
-struct KerpleWs { size_t wt, cexp, phi, dphi, dpart, total; };
+struct KerpleWs { size_t wt, cexp, phi, dphi, dpart, fft, total; };
 static KerpleWs kerple_ws(int B, int N, int H, int DH, int M, int backward) {
   KerpleWs w;
   size_t o = 0;
@@ -902,6 +907,7 @@ static KerpleWs kerple_ws(int B, int N, int H, int DH, int M, int backward) {
   w.phi = o; o += phi;
   w.dphi = o; if (backward) o += phi;
   w.dpart = o; if (backward) o += align_up((size_t)B * H * ((N + TQ - 1) / TQ) * (2 * N - 1) * sizeof(float), 256);
+  w.fft = o; if (!backward && kerple_fft_eligible(N, DH, M)) o += kerple_fft_ws_bytes(B, N, H, DH, M);
   w.total = o;
   return w;
 }
@@ -950,6 +956,14 @@ extern "C" int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_o
   if (workspace_bytes < w.total) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
+  if (kerple_fft_eligible(N, head_dim, M)) {  // long sequences: the reference's FFT route, fused with the read-out
+    rc = kerple_features(qkv, ws, w, omega, rel_pos_bias, B, N, H, head_dim, M, kind, dtype, st);
+    if (rc) return rc;
+    const int ld = (int)kerple_ldphi(M);
+    const float* phi = (const float*)(ws + w.phi);
+    return kerple_fft_forward(qkv, out, den_out, phi, phi + (size_t)B * H * N * ld, ld, (const float*)(ws + w.cexp),
+                              ws + w.fft, B, N, H, head_dim, M, dtype, st);
+  }
   if (ktile_tc_eligible(N, head_dim, M)) {  // tensor-core tiles: features computed in the tile, nothing staged in HBM
     rc = kerple_tables(ws, w, omega, rel_pos_bias, N, H, head_dim, M, kind, st);
     if (rc) return rc;

@@ -56,6 +56,7 @@ SIGNATURES = {
     "erv_block_ln_qkv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _Z, _P]),
     "erv_block_mlp_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P]),
     "erv_block_mlp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P, _Z, _P]),
+    "erv_kerple_set_fft": (None, [_I]),
     "erv_kerple_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_kerple_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_softmax_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, c_uint64, _P, _I, _P, _Z, _P]),

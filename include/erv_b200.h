@@ -184,6 +184,11 @@ int erv_head_loss_bwd(const float* x, const float* ln_w, const float* ln_b, cons
 int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_out, const float* omega,
                              const float* rel_pos_bias, int B, int N, int H, int head_dim, int M,
                              int kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* Route of erv_kerple_attention_fwd: 1 = the reference's FFT route (kerple.py:252-270 -> fft_utils.py:142-170: Toeplitz
+ * product by FFT along the patch axis, here a shared-memory radix-16 transform of 8192 points fused with the phi(q)
+ * read-out) whenever N - 1 <= 4096, 0 = Toeplitz-masked tiles always, -1 = default (FFT for N - 1 > 1024 and M > 64, the measured
+ * crossover, or the ERV_KERPLE_FFT environment variable).  Both routes compute the same function; the workspace query follows the mode. */
+void erv_kerple_set_fft(int mode);
 int erv_kerple_attention_bwd(const void* qkv, const void* out, const float* den, const void* dout,
                              void* dqkv, float* dbias, const float* omega, const float* rel_pos_bias,
                              int B, int N, int H, int head_dim, int M, int kind, int dtype,

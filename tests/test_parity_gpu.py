@@ -353,3 +353,55 @@ def test_softmax_dropout_draws_new_masks_on_graph_replay():
     o1, _ = ops.softmax_attention(qkv, 2, dropout_p=0.3, seed=seed)
     o2, _ = ops.softmax_attention(qkv, 2, dropout_p=0.3, seed=seed)
     assert torch.equal(o1, o2)
+
+
+# ---- KERPLE by FFT (erv_kerple_fft.cu): the reference's own route (kerple.py:252-270 -> fft_utils.py:142-170) ------------
+@pytest.fixture
+def kerple_fft_forced():
+    from erv_b200 import _capi
+    lib = _capi.load()
+    lib.erv_kerple_set_fft(1)
+    yield
+    lib.erv_kerple_set_fft(-1)
+
+
+@pytest.mark.parametrize("fname", [f for f in golden_files("attn_") if "most_general" in f])
+def test_kerple_fft_route_matches_reference(fname, kerple_fft_forced):
+    """Golden KERPLE cases with the forward forced onto the FFT route (the backward stays on the tile route and consumes
+    the FFT route's saved output / normaliser), fp32 and bf16 autocast."""
+    _, a, r = parse_attn_case(fname)
+    g = load_golden(fname)
+    attn, rpe = _build(g, a, r)
+    x = g["x"].to(DEV).requires_grad_(True)
+    out = attn(x, rpe=rpe)
+    assert_close(out, g["out"], TOL_F32, "out")
+    (out * g["cotangent"].to(DEV)).sum().backward()
+    assert_close(x.grad, g["dx"], TOL_F32, "dx")
+    for k, p in rpe.named_parameters():
+        assert_close(p.grad, g["grad.rpe." + k], TOL_F32, k)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out16 = attn(x.detach(), rpe=rpe)
+    assert out16.dtype == torch.bfloat16
+    assert rel_l2(out16.float(), g["out"]) < TOL_BF16
+
+
+@pytest.mark.parametrize("a,b,n,dim,heads,m", [
+    ("favor_plus", 2, 258, 32, 2, 44),    # 257 patches: zero padding inside the thread's first register
+    ("relu", 1, 1030, 32, 2, 33),         # odd feature count: the last transform carries one real column
+    ("favor_plus", 1, 600, 64, 2, 16),    # head_dim 32
+    ("favor_plus", 1, 4097, 32, 2, 44),   # config 5: all 4096 patches, circular length exactly 2*4096
+    ("relu", 3, 2050, 32, 2, 256),        # M = 256, default dispatch (N - 1 > 1024)
+])
+def test_kerple_fft_route_matches_oracle(a, b, n, dim, heads, m, kerple_fft_forced):
+    from erv_b200 import ATTENTION_REGISTRY, RPE_REGISTRY
+    from oracle import erv_oracle as O
+    torch.manual_seed(n + m)
+    attn = ATTENTION_REGISTRY[a](dim=dim, heads=heads, dropout=0.0, num_features=m)
+    rpe = RPE_REGISTRY["most_general"](num_patches=n, dim=dim, heads=heads)
+    with torch.no_grad():
+        rpe.rel_pos_bias.normal_(0.0, 0.3)
+    x = torch.randn(b, n, dim)
+    with torch.no_grad():
+        want = O.attention_forward(x, dict(attn.state_dict()), heads, ATTN_KIND[a], "kerple", dict(rpe.state_dict()), route="dense")
+        got = attn.to(DEV).eval()(x.to(DEV), rpe=rpe.to(DEV))
+    assert_close(got, want, TOL_F32, "out")

@@ -10,8 +10,8 @@ cap() {  # kernel-regex tag skip bench-args...
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs "$@" > gpurun_out/plain_${TAG}_$t.log 2>&1 || { echo "plain $t failed"; return; }
   ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -f -o gpurun_out/prof_${TAG}_$t python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs "$@" > gpurun_out/ncu_${TAG}_$t.log 2>&1
 }
-cap la_tc2_fwd_kernel fwd 4
-cap la_tc2_bwd_kernel bwd 4
+cap la_pipe_fwd_kernel fwd 4
+cap la_pipe_bwd_kernel bwd 4
 cap ktile_fwd_kernel k3fwd 3 --workload config3 --batch 1024
 cap ktile_bwd_kernel k3bwd 3 --workload config3 --batch 1024
 cap stile_fwd_kernel s4fwd 3 --workload config4b --batch 256
