@@ -19,6 +19,9 @@ namespace erv {
 template <typename T, int DH, int NC>
 __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs p) {
   using C = TcCfg<DH>;
+  // bf16 inputs (autocast, budget 2e-2): the contractions use the hi images only -- one bf16 product instead of the three
+  // split terms the fp32 path needs for 1e-4; the projection keeps 3xTF32 (it feeds exp)
+  constexpr int kTerms = sizeof(T) == 2 ? 1 : 3;
   constexpr int ND = C::ND;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;  // G1 completions / G2-G4 completions
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
             const int ksteps = nt16 / 16;
             for (int rb = 0; rb < nrb; ++rb) {
               bool acc = n0 > 0;
-              for (int term = 0; term < 3; ++term) {
+              for (int term = 0; term < kTerms; ++term) {
                 const uint8_t* a_img = (term == 2) ? phi2 : phi1;
                 const uint8_t* b_img = (term == 1) ? v2 : v1;
                 for (int s = 0; s < ksteps; ++s) {
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
             }
           } else {  // G4: [num|den] = phi [S|z]
             bool acc = false;
-            for (int term = 0; term < 3; ++term) {
+            for (int term = 0; term < kTerms; ++term) {
               const uint8_t* a_img = (term == 2) ? phi2 : phi1;
               const uint8_t* b_img = (term == 1) ? s2 : s1;
               for (int s = 0; s < Mp / 16; ++s) {

@@ -48,6 +48,9 @@ __device__ __forceinline__ void unpack8(const uint8_t* hi_img, const uint8_t* lo
 template <typename T, int DH, int NRB, int CPH>
 __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdArgs p) {
   using C = TcCfg<DH>;
+  // bf16 inputs (autocast, budget 2e-2): the contractions use the hi images only -- one bf16 product instead of the three
+  // split terms the fp32 path needs for 1e-4; the projection keeps 3xTF32 (it feeds exp)
+  constexpr int kTerms = sizeof(T) == 2 ? 1 : 3;
   constexpr int ND = C::ND, RW = DH + 4;
   constexpr uint32_t COL_P = 0, COL_S = 256;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
         if (pass == 2 && warp == 0 && elect_one()) {  // K2: dphi_k = [v|1] [dS|dz]^T can start as soon as P has been consumed
           fence_after_sync();
           bool acc = false;
-          for (int term = 0; term < 3; ++term) {
+          for (int term = 0; term < kTerms; ++term) {
             const uint8_t* a_img = (term == 2) ? av2 : av1;
             const uint8_t* b_img = (term == 1) ? s2 : s1;
             for (int s = 0; s < ND / 16; ++s) {
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
           if (warp == 0 && elect_one()) {
             fence_after_sync();
             bool acc = !first;
-            for (int term = 0; term < 3; ++term) {
+            for (int term = 0; term < kTerms; ++term) {
               const uint8_t* a_img = (term == 2) ? phi2 : phi1;
               const uint8_t* b_img = (term == 1) ? av2 : av1;
               for (int s = 0; s < nt16 / 16; ++s) {
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
             if (warp == 0 && elect_one()) {
               if (hb == nrb - 1) {  // dphi_q for the whole row, into the (consumed) P columns
                 bool acc = false;
-                for (int term = 0; term < 3; ++term) {
+                for (int term = 0; term < kTerms; ++term) {
                   const uint8_t* a_img = (term == 2) ? av2 : av1;
                   const uint8_t* b_img = (term == 1) ? s2 : s1;
                   for (int s = 0; s < ND / 16; ++s) {
