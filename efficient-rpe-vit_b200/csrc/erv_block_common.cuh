@@ -39,6 +39,7 @@ struct MlpArgs {
   float* da; float* dx1; float* part;  // bwd out
   const long long* seed; int salt;
   int R; float eps, p_drop;
+  int act_bf16;                     // a / da are bf16 (autocast) instead of fp32: tcgen05 family only
 };
 
 // out[k] = sum over CTAs of part[cta][k] (fixed order); with dst the sums are added to the segment buffers instead

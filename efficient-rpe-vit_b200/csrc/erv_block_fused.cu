@@ -472,33 +472,33 @@ __global__ void __launch_bounds__(THREADS, 2) mlp_bwd_kernel(const MlpArgs p) {
   }
 }
 
-// out[k] = sum over CTAs of part[cta][k] in a fixed order: 32 entries per CTA, 8 slices of the partial list per entry.
+// out[k] = sum over CTAs of part[cta][k] in a fixed order: 32 entries per CTA, 32 slices of the partial list per entry.
 // With `dst` (one pointer per parameter segment, segment s = entries [seg[s], seg[s+1])) the sums are ADDED to the
 // parameters' gradient buffers instead (fused gradient accumulation); a null segment pointer is skipped.
 struct SumArgs {
   const float* part; float* out; int n, P, nseg;
   float* dst[8]; int seg[9];
 };
-__global__ void __launch_bounds__(256) sum_partials_kernel(const SumArgs a) {
-  __shared__ float sh[8][32];
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const SumArgs a) {
+  // 32 entries x 32 slices of the partial list per CTA: every thread has at most ceil(n / 32) independent loads in flight
+  // (n <= 296 partial rows), the slices are combined in a fixed order
+  __shared__ float sh[32][33];
   const int kx = threadIdx.x & 31, sl = threadIdx.x >> 5, k = blockIdx.x * 32 + kx;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s0 = 0.f, s1 = 0.f;
   if (k < a.P) {
     int c = sl;
-    for (; c + 24 < a.n; c += 32) {
+    for (; c + 32 < a.n; c += 64) {
       s0 += a.part[(size_t)c * a.P + k];
-      s1 += a.part[(size_t)(c + 8) * a.P + k];
-      s2 += a.part[(size_t)(c + 16) * a.P + k];
-      s3 += a.part[(size_t)(c + 24) * a.P + k];
+      s1 += a.part[(size_t)(c + 32) * a.P + k];
     }
-    for (; c < a.n; c += 8) s0 += a.part[(size_t)c * a.P + k];
+    if (c < a.n) s0 += a.part[(size_t)c * a.P + k];
   }
-  sh[sl][kx] = (s0 + s1) + (s2 + s3);
+  sh[sl][kx] = s0 + s1;
   __syncthreads();
   if (sl == 0 && k < a.P) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += sh[i][kx];
+    for (int i = 0; i < 32; ++i) s += sh[i][kx];
     if (a.nseg == 0) {
       a.out[k] = s;
     } else {
@@ -515,7 +515,7 @@ int launch_sum(const float* part, float* out, int n, int P, float* const* dst, c
     for (int g = 0; g < nseg; ++g) a.dst[g] = dst[g];
     for (int g = 0; g <= nseg; ++g) a.seg[g] = seg[g];
   }
-  sum_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(a);
+  sum_partials_kernel<<<(P + 31) / 32, 1024, 0, st>>>(a);
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }
@@ -537,7 +537,7 @@ int launch_mlp_bwd_tc(const MlpArgs& a, int max_ctas, cudaStream_t st, int* grid
 int launch_mlp_fwd_tc(const MlpArgs& a, cudaStream_t st);
 int launch_ln_qkv_tc(bool bwd, const float* x, const float* ln_w, const float* ln_b, const float* w, const float* b, float* qkv,
                      const float* dqkv, const float* dres, float* dx, float* part, int rows, float eps, int max_ctas,
-                     cudaStream_t st, int* grid_out);
+                     cudaStream_t st, int* grid_out, int act_bf16);
 }  // namespace blk
 }  // namespace erv
 
@@ -557,14 +557,26 @@ static bool aligned16(std::initializer_list<const void*> ptrs) {
   return true;
 }
 
+// act_dtype: ERV_F32 or ERV_BF16 (tcgen05 family only) = element type of the activations exchanged with the attention core
+static int check_act(const char* fn, int act_dtype) {
+  if (act_dtype == ERV_F32) return ERV_OK;
+  if (act_dtype == ERV_BF16 && mlp_bwd_tc_enabled()) return ERV_OK;
+  set_error("%s: activation dtype %d unsupported (bf16 needs the tensor-core block kernels)", fn, act_dtype);
+  return ERV_E_UNSUPPORTED;
+}
+extern "C" int erv_block_act_bf16_supported(void) { return mlp_bwd_tc_enabled() ? 1 : 0; }
+
 extern "C" int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,
-                                    const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream) {
+                                    const float* b_qkv, void* qkv_out, int act_dtype, int rows, int dim, float eps,
+                                    void* stream) {
+  float* qkv = static_cast<float*>(qkv_out);
   ERV_CHECK_ARG(x && ln_w && ln_b && w_qkv && qkv && rows > 0, "erv_block_ln_qkv_fwd: bad arguments");
+  if (int rc = check_act("erv_block_ln_qkv_fwd", act_dtype)) return rc;
   ERV_CHECK_ARG(aligned16({x, ln_w, ln_b, w_qkv, b_qkv, qkv}), "erv_block_ln_qkv_fwd: pointers must be 16-byte aligned");
   if (dim != C) { set_error("erv_block_ln_qkv_fwd: dim %d not supported (32)", dim); return ERV_E_UNSUPPORTED; }
   if (mlp_bwd_tc_enabled())  // tcgen05 tiles (erv_block_tc.cu)
     return launch_ln_qkv_tc(false, x, ln_w, ln_b, w_qkv, b_qkv, qkv, nullptr, nullptr, nullptr, nullptr, rows, eps, 0,
-                            (cudaStream_t)stream, nullptr);
+                            (cudaStream_t)stream, nullptr, act_dtype == ERV_BF16);
   LnQkvArgs a{};
   a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.w = w_qkv; a.b = b_qkv; a.qkv = qkv; a.R = rows; a.eps = eps;
   const size_t smem = (size_t)(QKV * C + WARPS * T * C) * sizeof(float);
@@ -574,10 +586,12 @@ extern "C" int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const flo
   return ERV_OK;
 }
 
-extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, const float* ln_w,
+extern "C" int erv_block_ln_qkv_bwd(const float* x, const void* dqkv_in, int act_dtype, const float* dres, const float* ln_w,
                                     const float* ln_b, const float* w_qkv, float* dx, float* dparams,
                                     float* const* grad_accum, int rows, int dim, float eps, void* workspace,
                                     size_t workspace_bytes, void* stream) {
+  const float* dqkv = static_cast<const float*>(dqkv_in);
+  if (int rc = check_act("erv_block_ln_qkv_bwd", act_dtype)) return rc;
   ERV_CHECK_ARG(x && dqkv && ln_w && ln_b && w_qkv && dx && (dparams || grad_accum) && workspace && rows > 0,
                 "erv_block_ln_qkv_bwd: bad arguments");
   ERV_CHECK_ARG(aligned16({x, dqkv, dres, ln_w, ln_b, w_qkv, dx, workspace}), "erv_block_ln_qkv_bwd: pointers must be 16-byte aligned");
@@ -587,7 +601,7 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
   if (mlp_bwd_tc_enabled()) {  // tcgen05 tiles (erv_block_tc.cu)
     int tc_grid = 0;
     int rc = launch_ln_qkv_tc(true, x, ln_w, ln_b, w_qkv, nullptr, nullptr, dqkv, dres, dx, (float*)workspace, rows, eps,
-                              grid_for(rows, TILE), (cudaStream_t)stream, &tc_grid);
+                              grid_for(rows, TILE), (cudaStream_t)stream, &tc_grid, act_dtype == ERV_BF16);
     if (rc) return rc;
     return launch_sum((const float*)workspace, dparams, tc_grid, P_QKV, grad_accum, seg, 4, (cudaStream_t)stream);
   }
@@ -604,7 +618,9 @@ extern "C" int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const flo
 }
 
 static int fill_mlp(MlpArgs& a, const char* fn, const float* attn_out, const float* x, const float* const* params, int rows,
-                    int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt) {
+                    int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt, int act_dtype) {
+  if (int rc = check_act(fn, act_dtype)) return rc;
+  a.act_bf16 = act_dtype == ERV_BF16;
   ERV_CHECK_ARG(attn_out && x && params && rows > 0, "%s: bad arguments", fn);
   for (int i = 0; i < 8; ++i) ERV_CHECK_ARG(params[i], "%s: parameter %d is null", fn, i);
   for (int i = 0; i < 8; ++i) ERV_CHECK_ARG(aligned16({params[i]}), "%s: parameter %d must be 16-byte aligned", fn, i);
@@ -618,11 +634,12 @@ static int fill_mlp(MlpArgs& a, const char* fn, const float* attn_out, const flo
   return ERV_OK;
 }
 
-extern "C" int erv_block_mlp_fwd(const float* attn_out, const float* x, const float* const* params, float* y, int rows,
-                                 int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt,
+extern "C" int erv_block_mlp_fwd(const void* attn_out, int act_dtype, const float* x, const float* const* params, float* y,
+                                 int rows, int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt,
                                  void* stream) {
   MlpArgs a{};
-  int rc = fill_mlp(a, "erv_block_mlp_fwd", attn_out, x, params, rows, dim, mlp_dim, eps, p_drop, seed, salt);
+  int rc = fill_mlp(a, "erv_block_mlp_fwd", static_cast<const float*>(attn_out), x, params, rows, dim, mlp_dim, eps, p_drop, seed,
+                    salt, act_dtype);
   if (rc) return rc;
   ERV_CHECK_ARG(y && aligned16({y}), "erv_block_mlp_fwd: null or misaligned output");
   a.y = y;
@@ -634,12 +651,14 @@ extern "C" int erv_block_mlp_fwd(const float* attn_out, const float* x, const fl
   return ERV_OK;
 }
 
-extern "C" int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, const float* const* params,
-                                 float* d_attn_out, float* dx1, float* dparams, float* const* grad_accum, int rows, int dim,
-                                 int mlp_dim, float eps, float p_drop, const long long* seed, int salt, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+extern "C" int erv_block_mlp_bwd(const void* attn_out, int act_dtype, const float* x, const float* dy,
+                                 const float* const* params, void* d_attn_out_v, float* dx1, float* dparams,
+                                 float* const* grad_accum, int rows, int dim, int mlp_dim, float eps, float p_drop,
+                                 const long long* seed, int salt, void* workspace, size_t workspace_bytes, void* stream) {
   MlpArgs a{};
-  int rc = fill_mlp(a, "erv_block_mlp_bwd", attn_out, x, params, rows, dim, mlp_dim, eps, p_drop, seed, salt);
+  float* d_attn_out = static_cast<float*>(d_attn_out_v);
+  int rc = fill_mlp(a, "erv_block_mlp_bwd", static_cast<const float*>(attn_out), x, params, rows, dim, mlp_dim, eps, p_drop, seed,
+                    salt, act_dtype);
   if (rc) return rc;
   ERV_CHECK_ARG(dy && d_attn_out && dx1 && (dparams || grad_accum) && workspace, "erv_block_mlp_bwd: null pointer");
   ERV_CHECK_ARG(aligned16({dy, d_attn_out, dx1, workspace}), "erv_block_mlp_bwd: pointers must be 16-byte aligned");

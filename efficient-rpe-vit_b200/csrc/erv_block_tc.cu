@@ -90,6 +90,26 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
   st4(p, make_float4(v[0], v[1], v[2], v[3]));
   st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
 }
+// activations the attention core produces / consumes (qkv, dqkv, attention output and its gradient) are bf16 under autocast:
+// 8 elements = one 16-byte load / store, converted in registers (no separate cast kernels)
+__device__ __forceinline__ void ld8a(const float* p, size_t idx, bool bf16, float (&v)[8]) {
+  if (!bf16) { ld8(p + idx, v); return; }
+  const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void st8a(float* p, size_t idx, bool bf16, const float (&v)[8]) {
+  if (!bf16) { st8(p + idx, v); return; }
+  uint4 raw;
+  uint32_t* w = &raw.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + idx) = raw;
+}
 // 8 fp32 TMEM columns of the caller's lane, summed over the three column groups of a row product
 __device__ __forceinline__ void tmem_sum3(uint32_t t0, uint32_t stride, float (&v)[8]) {
   uint32_t r0[8], r1[8], r2[8];
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
 #pragma unroll
     for (int i = 0; i < 8; ++i) na[i] = nx[i] = ndy[i] = 0.f;
     if (tile < ntiles && rr < p.R) {
-      ld8(p.a + (size_t)rr * C + c0, na);
+      ld8a(p.a, (size_t)rr * C + c0, p.act_bf16 != 0, na);
       ld8(p.x + (size_t)rr * C + c0, nx);
       ld8(p.dy + (size_t)rr * C + c0, ndy);
     }
@@ -395,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_bwd_tc_kernel(const MlpArgs
     {
       float da[8];
       tmem_sum3(tm + lane_off + COL_G + 96 + c0, 32, da);
-      if (valid) st8(p.da + (size_t)r * C + c0, da);
+      if (valid) st8a(p.da, (size_t)r * C + c0, p.act_bf16 != 0, da);
     }
     fence_before_sync();
     __syncthreads();  // exchange buffers and the product columns are reused by the next tile
@@ -522,7 +542,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_fwd_tc_kernel(const MlpArgs
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = x[i] = 0.f;
     if (tile < ntiles && r < p.R) {
-      ld8(p.a + (size_t)r * C + c0, a);
+      ld8a(p.a, (size_t)r * C + c0, p.act_bf16 != 0, a);
       ld8(p.x + (size_t)r * C + c0, x);
     }
   };
@@ -591,6 +611,7 @@ struct LnQkvTcArgs {
   const float* dqkv; const float* dres;  // backward inputs (dres may be null)
   float* dx; float* part;
   int R; float eps;
+  int act_bf16;  // qkv / dqkv are bf16 (autocast) instead of fp32
 };
 // forward: the 96 outputs are produced as two 48-wide halves (3 x 96 columns would not fit one instruction's N <= 256)
 constexpr uint32_t Q_N = 0, Q_END = 12, Q_W = Q_END * CH, Q_WHALF = 4 * 2304, Q_SMEM = Q_W + 2 * Q_WHALF;  // 42 KB
@@ -657,7 +678,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_fwd_tc_kernel(const LnQk
       tmem_sum3(tm + lane_off + qbase + 8 * k, 48, o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += bq[8 * k + i];
-      if (r < p.R) st8(p.qkv + (size_t)r * QKV + q0 + 8 * k, o);
+      if (r < p.R) st8a(p.qkv, (size_t)r * QKV + q0 + 8 * k, p.act_bf16 != 0, o);
     }
     fence_before_sync();
     __syncthreads();
@@ -714,7 +735,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_qkv_bwd_tc_kernel(const LnQk
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float t[8];
-        ld8(p.dqkv + (size_t)rr * QKV + q0 + 8 * k, t);
+        ld8a(p.dqkv, (size_t)rr * QKV + q0 + 8 * k, p.act_bf16 != 0, t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) ndq[8 * k + i] = t[i];
       }
@@ -1065,10 +1086,10 @@ int launch_mlp_fwd_tc(const MlpArgs& a, cudaStream_t st) {
 }
 int launch_ln_qkv_tc(bool bwd, const float* x, const float* ln_w, const float* ln_b, const float* w, const float* b, float* qkv,
                      const float* dqkv, const float* dres, float* dx, float* part, int rows, float eps, int max_ctas,
-                     cudaStream_t st, int* grid_out) {
+                     cudaStream_t st, int* grid_out, int act_bf16) {
   LnQkvTcArgs a{};
   a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.w = w; a.b = b; a.qkv = qkv; a.dqkv = dqkv; a.dres = dres; a.dx = dx; a.part = part;
-  a.R = rows; a.eps = eps;
+  a.R = rows; a.eps = eps; a.act_bf16 = act_bf16;
   const int ntiles = (rows + 127) / 128;
   int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
   if (bwd && grid > max_ctas) grid = max_ctas;

@@ -33,6 +33,7 @@ constexpr int NT = 512;        // threads per CTA: 16 points each
 constexpr int NP_MAX = 4096;   // patches per sequence this length serves
 constexpr int XROW = 33;       // padded row of the second exchange (32 points + 1)
 constexpr size_t kSmem = (size_t)256 * XROW * sizeof(float2);  // 67 584 B >= 8192 points
+constexpr size_t kSmemFwd = kSmem + 2 * (size_t)NP_MAX * sizeof(float2);  // + the phi_k / phi_q staging slots
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -203,20 +204,40 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
     vv[r] = 0.f;
     if (i < NP) vv[r] = d < p.DH ? to_f(static_cast<const T*>(p.qkv)[qkv_off(b, i + 1, 2, h, N, p.H, p.DH) + d]) : 1.f;
   }
+  // phi_k[., m..m+1] of the next feature pair and phi_q[., m..m+1] of the current one are staged with 8-byte cp.async into
+  // per-thread slots of shared memory (thread t copies and later reads only elements t + 512 r), so the strided global
+  // reads are in flight under the two transforms instead of in front of them
+  float2* stage_k = sm + 256 * XROW;
+  float2* stage_q = stage_k + NP_MAX;
+  auto stage = [&](float2* dst, const float* src, int m) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = t + 512 * r;
+      if (i < NP)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)),
+                     "l"(src + (size_t)(i + 1) * ld + m) : "memory");
+    }
+  };
   const int fp0 = chunk * p.fp_per_chunk, fp1 = min(fp0 + p.fp_per_chunk, (p.M + 1) / 2);
+  if (fp0 < fp1) stage(stage_k, pk, 2 * fp0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
   for (int fp = fp0; fp < fp1; ++fp) {
     const int m = 2 * fp;
     const bool two = m + 1 < p.M;
     float2 x[16];
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;
       float2 f = make_float2(0.f, 0.f);
-      if (i < NP) f = __ldg(reinterpret_cast<const float2*>(pk + (size_t)(i + 1) * ld + m));
+      if (i < NP) f = stage_k[i];
       if (!two) f.y = 0.f;
       x[r] = make_float2(vv[r] * f.x, vv[r] * f.y);
       x[r + 8] = make_float2(0.f, 0.f);
     }
+    if (fp + 1 < fp1) stage(stage_k, pk, m + 2);
+    stage(stage_q, pq, m);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
     fft8192(x, sm, w);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -224,11 +245,12 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
       x[q] = make_float2(y.x, -y.y);  // inverse transform as conj(DFT(conj(.)))
     }
     fft8192(x, sm, w);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;
       if (i < NP) {
-        float2 f = __ldg(reinterpret_cast<const float2*>(pq + (size_t)(i + 1) * ld + m));
+        float2 f = stage_q[i];
         if (!two) f.y = 0.f;
         acc[r] = fmaf(f.x, x[r].x, acc[r]);
         acc[r] = fmaf(-f.y, x[r].y, acc[r]);
@@ -370,11 +392,11 @@ int kerple_fft_forward(const void* qkv, void* out, float* den, const float* phi_
   ERV_LAUNCH_CHECK();
   const dim3 grid(a.chunks, DH + 1, B * H);
   if (dtype == ERV_F32) {
-    ERV_CUDA(allow_smem(kfft::kfft_fwd_kernel<float>, kfft::kSmem));
-    kfft::kfft_fwd_kernel<float><<<grid, kfft::NT, kfft::kSmem, st>>>(a);
+    ERV_CUDA(allow_smem(kfft::kfft_fwd_kernel<float>, kfft::kSmemFwd));
+    kfft::kfft_fwd_kernel<float><<<grid, kfft::NT, kfft::kSmemFwd, st>>>(a);
   } else {
-    ERV_CUDA(allow_smem(kfft::kfft_fwd_kernel<__nv_bfloat16>, kfft::kSmem));
-    kfft::kfft_fwd_kernel<__nv_bfloat16><<<grid, kfft::NT, kfft::kSmem, st>>>(a);
+    ERV_CUDA(allow_smem(kfft::kfft_fwd_kernel<__nv_bfloat16>, kfft::kSmemFwd));
+    kfft::kfft_fwd_kernel<__nv_bfloat16><<<grid, kfft::NT, kfft::kSmemFwd, st>>>(a);
   }
   ERV_LAUNCH_CHECK();
 #define ERV_KFFT_TAIL(DHV)                                                                                      \

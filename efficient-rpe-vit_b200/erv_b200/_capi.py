@@ -52,10 +52,11 @@ SIGNATURES = {
     "erv_block_mlp_params": (c_int, []),
     "erv_block_ln_qkv_bwd_workspace": (c_size_t, [_I]),
     "erv_block_mlp_bwd_workspace": (c_size_t, [_I]),
-    "erv_block_ln_qkv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
-    "erv_block_ln_qkv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _Z, _P]),
-    "erv_block_mlp_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P]),
-    "erv_block_mlp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P, _Z, _P]),
+    "erv_block_act_bf16_supported": (c_int, []),
+    "erv_block_ln_qkv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "erv_block_ln_qkv_bwd": (c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _Z, _P]),
+    "erv_block_mlp_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P]),
+    "erv_block_mlp_bwd": (c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _I, _P, _Z, _P]),
     "erv_kerple_set_fft": (None, [_I]),
     "erv_kerple_attention_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "erv_kerple_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),

@@ -501,47 +501,64 @@ def dropout_seed(device):
 
 class _BlockLnQkv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w, b, eps):
+    def forward(ctx, x, ln_w, ln_b, w, b, eps, out_dtype):
         C.require_cuda(x, ln_w, ln_b, w)
         dim = x.shape[-1]
         x2 = x.reshape(-1, dim).contiguous()
         rows = x2.shape[0]
-        qkv = torch.empty(rows, 3 * dim, device=x.device, dtype=torch.float32)
-        C.check(C.load().erv_block_ln_qkv_fwd(C.ptr(x2), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(qkv), rows, dim,
-                                              float(eps), C.stream()), "block_ln_qkv")
+        lib = C.load()
+        # bf16 autocast: the kernel writes the bf16 qkv an autocast Linear would hand the attention core (no cast kernel)
+        direct = out_dtype == torch.bfloat16 and lib.erv_block_act_bf16_supported()
+        qkv = torch.empty(rows, 3 * dim, device=x.device, dtype=torch.bfloat16 if direct else torch.float32)
+        C.check(lib.erv_block_ln_qkv_fwd(C.ptr(x2), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(b), C.ptr(qkv), C.dtype_code(qkv),
+                                         rows, dim, float(eps), C.stream()), "block_ln_qkv")
+        if out_dtype is not None and qkv.dtype != out_dtype:
+            qkv = qkv.to(out_dtype)
         ctx.save_for_backward(x2, ln_w, ln_b, w, b)
         ctx.meta = (x.shape, float(eps), b is not None)
-        return qkv.reshape(*x.shape[:-1], 3 * dim)
+        # the block input is handed on as a second output: the residual branch reads it from here, so its gradient arrives in
+        # this backward and is added inside the kernel (dres) instead of by an autograd accumulation kernel
+        return qkv.reshape(*x.shape[:-1], 3 * dim), x.view_as(x)
 
     @staticmethod
-    def backward(ctx, dqkv):
+    def backward(ctx, dqkv, dres):
         x2, ln_w, ln_b, w, b = ctx.saved_tensors
         shape, eps, has_bias = ctx.meta
         rows, dim = x2.shape
         lib = C.load()
-        dq = dqkv.reshape(rows, 3 * dim).to(torch.float32).contiguous()
+        if dqkv is None:
+            dqkv = torch.zeros(rows, 3 * dim, device=x2.device, dtype=torch.float32)
+        dq = dqkv.reshape(rows, 3 * dim)
+        if not (dq.dtype == torch.bfloat16 and lib.erv_block_act_bf16_supported()):
+            dq = dq.to(torch.float32)
+        dq = dq.contiguous()
+        if dres is not None:
+            dres = dres.reshape(rows, dim).to(torch.float32).contiguous()
         dx = torch.empty_like(x2)
         nbytes = lib.erv_block_ln_qkv_bwd_workspace(rows)
         ws = C.workspace(nbytes, x2.device)
         tgt = _grad_targets((w, b, ln_w, ln_b))
         dpar = None if tgt else torch.empty(lib.erv_block_ln_qkv_params(), device=x2.device, dtype=torch.float32)
-        C.check(lib.erv_block_ln_qkv_bwd(C.ptr(x2), C.ptr(dq), None, C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(dx), C.ptr(dpar),
+        C.check(lib.erv_block_ln_qkv_bwd(C.ptr(x2), C.ptr(dq), C.dtype_code(dq), C.ptr(dres), C.ptr(ln_w), C.ptr(ln_b), C.ptr(w), C.ptr(dx), C.ptr(dpar),
                                          _ptr_array(tgt) if tgt else None, rows, dim, eps, C.ptr(ws), nbytes, C.stream()),
                 "block_ln_qkv_bwd")
         if tgt:
-            return dx.reshape(shape), None, None, None, None, None
+            return dx.reshape(shape), None, None, None, None, None, None
         nw = 3 * dim * dim
         dw = dpar[:nw].view(3 * dim, dim)
         db = dpar[nw:nw + 3 * dim] if has_bias else None
-        return dx.reshape(shape), dpar[nw + 3 * dim:nw + 4 * dim], dpar[nw + 4 * dim:nw + 5 * dim], dw, db, None
+        return dx.reshape(shape), dpar[nw + 3 * dim:nw + 4 * dim], dpar[nw + 4 * dim:nw + 5 * dim], dw, db, None, None
 
 
 def block_supported(dim: int, mlp_dim: int) -> bool:
     return bool(C.load().erv_block_supported(int(dim), int(mlp_dim)))
 
 
-def block_ln_qkv(x, ln_w, ln_b, w, b, eps=1e-5):
-    return _BlockLnQkv.apply(x, ln_w, ln_b, w, b, eps)
+def block_ln_qkv(x, ln_w, ln_b, w, b, eps=1e-5, with_residual=False, out_dtype=None):
+    """qkv = LayerNorm(x) W^T (+ b), fp32 or (out_dtype=torch.bfloat16, autocast) bf16.  with_residual=True also returns x itself
+    for the residual branch (see _BlockLnQkv)."""
+    qkv, xr = _BlockLnQkv.apply(x, ln_w, ln_b, w, b, eps, out_dtype)
+    return (qkv, xr) if with_residual else qkv
 
 
 def _param_array(params):
@@ -553,13 +570,17 @@ class _BlockMlp(torch.autograd.Function):
     def forward(ctx, a, x, wp, bp, ln_w, ln_b, w1, b1, w2, b2, eps, p_drop, seed, salt):
         C.require_cuda(a, x, wp)
         dim, mlp_dim = x.shape[-1], w1.shape[0]
-        a2 = a.reshape(-1, dim).to(torch.float32).contiguous()
+        lib = C.load()
+        a2 = a.reshape(-1, dim)
+        if not (a2.dtype == torch.bfloat16 and lib.erv_block_act_bf16_supported()):
+            a2 = a2.to(torch.float32)
+        a2 = a2.contiguous()
         x2 = x.reshape(-1, dim).contiguous()
         rows = x2.shape[0]
         params = (wp, bp, ln_w, ln_b, w1, b1, w2, b2)
         y = torch.empty_like(x2)
-        C.check(C.load().erv_block_mlp_fwd(C.ptr(a2), C.ptr(x2), _param_array(params), C.ptr(y), rows, dim, mlp_dim, float(eps),
-                                           float(p_drop), C.ptr(seed), int(salt), C.stream()), "block_mlp")
+        C.check(lib.erv_block_mlp_fwd(C.ptr(a2), C.dtype_code(a2), C.ptr(x2), _param_array(params), C.ptr(y), rows, dim, mlp_dim,
+                                      float(eps), float(p_drop), C.ptr(seed), int(salt), C.stream()), "block_mlp")
         ctx.save_for_backward(a2, x2, seed, *params)
         ctx.meta = (x.shape, float(eps), float(p_drop), int(salt), mlp_dim)
         ctx.a_dtype = a.dtype
@@ -577,7 +598,7 @@ class _BlockMlp(torch.autograd.Function):
         ws = C.workspace(nbytes, x2.device)
         tgt = _grad_targets(params)
         dpar = None if tgt else torch.empty(lib.erv_block_mlp_params(), device=x2.device, dtype=torch.float32)
-        C.check(lib.erv_block_mlp_bwd(C.ptr(a2), C.ptr(x2), C.ptr(dy2), _param_array(params), C.ptr(da), C.ptr(dx1), C.ptr(dpar),
+        C.check(lib.erv_block_mlp_bwd(C.ptr(a2), C.dtype_code(a2), C.ptr(x2), C.ptr(dy2), _param_array(params), C.ptr(da), C.ptr(dx1), C.ptr(dpar),
                                       _ptr_array(tgt) if tgt else None, rows, dim, mlp_dim, eps, p_drop, C.ptr(seed), salt,
                                       C.ptr(ws), nbytes, C.stream()), "block_mlp_bwd")
         da = da.reshape(shape).to(ctx.a_dtype)

@@ -56,11 +56,10 @@ class UnifiedTransformerBlock(nn.Module):
     def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
         att = self.attention
         att.before_qkv(x.shape, self.rpe)
-        qkv = ops.block_ln_qkv(x, self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, self.norm1.eps)
-        if torch.is_autocast_enabled():
-            # bf16 autocast: the attention core sees the bf16 qkv an autocast Linear would hand it; LayerNorm, the
-            # projections and the MLP stay in fp32 (more accurate than the reference's autocast run, same interface)
-            qkv = qkv.to(torch.bfloat16)
+        # bf16 autocast: the attention core sees the bf16 qkv an autocast Linear would hand it (written directly by the
+        # kernel); LayerNorm, the projections and the MLP stay in fp32 (more accurate than the reference's autocast run)
+        qkv, x = ops.block_ln_qkv(x, self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, self.norm1.eps,
+                                  with_residual=True, out_dtype=torch.bfloat16 if torch.is_autocast_enabled() else None)
         a = att.core(qkv, x.shape, self.rpe)
         p = self.mlp[2].p if self.training else 0.0
         seed = ops.dropout_seed(x.device) if p > 0 else None

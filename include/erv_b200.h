@@ -120,17 +120,22 @@ int erv_block_supported(int dim, int mlp_dim);
 /* Kernel family behind the four block calls: 1 = tcgen05 tiles (default), 0 = fp32 FFMA2 register tiles,
  * -1 = default / ERV_DISABLE_BLOCK_TC environment variable.  Both compute the same functions. */
 void erv_block_set_tensor_core(int mode);
+/* act_dtype (ERV_F32 / ERV_BF16) in the four calls below is the element type of the activations exchanged with the
+ * attention core: qkv, dqkv, attn_out, d_attn_out.  ERV_BF16 is what a bf16-autocast nn.Linear hands the core
+ * (favor_plus.py:174 under torch.autocast); the kernels convert in registers, so no cast kernels run around the core.
+ * bf16 needs the tcgen05 family (erv_block_act_bf16_supported() == 1); x, y, dx, dy and all parameters stay fp32. */
+int erv_block_act_bf16_supported(void);
 /* qkv [rows, 3*dim] = LayerNorm(x; ln_w, ln_b, eps) w_qkv^T (+ b_qkv, may be NULL): norm1 + attention.qkv
- * (unified_transformer.py:75-83, favor_plus.py:174).  fp32, x [rows, dim]. */
+ * (unified_transformer.py:75-83, favor_plus.py:174).  x [rows, dim] fp32. */
 int erv_block_ln_qkv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w_qkv,
-                         const float* b_qkv, float* qkv, int rows, int dim, float eps, void* stream);
+                         const float* b_qkv, void* qkv, int act_dtype, int rows, int dim, float eps, void* stream);
 /* Backward: dx = dres (may be NULL) + d/dx ; dparams [erv_block_ln_qkv_params()] = dW_qkv [3 dim, dim] |
  * db_qkv [3 dim] | dln_w [dim] | dln_b [dim].  Recomputes the LayerNorm from x.  With grad_accum (4 pointers
  * in that order, entries may be NULL) the parameter gradients are ADDED to those buffers instead and dparams
  * may be NULL (fused accumulation into .grad). */
 int erv_block_ln_qkv_params(void);
 size_t erv_block_ln_qkv_bwd_workspace(int rows);
-int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, const float* ln_w,
+int erv_block_ln_qkv_bwd(const float* x, const void* dqkv, int act_dtype, const float* dres, const float* ln_w,
                          const float* ln_b, const float* w_qkv, float* dx, float* dparams,
                          float* const* grad_accum, int rows, int dim, float eps, void* workspace,
                          size_t workspace_bytes, void* stream);
@@ -139,18 +144,18 @@ int erv_block_ln_qkv_bwd(const float* x, const float* dqkv, const float* dres, c
  * unified_transformer.py:85-88).  params = {w_proj, b_proj, ln_w, ln_b, w_fc1, b_fc1, w_fc2, b_fc2}
  * (nn.Linear layouts).  Dropout masks are a counter hash of (*seed, salt, element); seed is a device
  * pointer (CUDA-graph friendly) and may be NULL when p_drop == 0. */
-int erv_block_mlp_fwd(const float* attn_out, const float* x, const float* const* params, float* y, int rows,
-                      int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt,
+int erv_block_mlp_fwd(const void* attn_out, int act_dtype, const float* x, const float* const* params, float* y,
+                      int rows, int dim, int mlp_dim, float eps, float p_drop, const long long* seed, int salt,
                       void* stream);
 /* Backward: recomputes the forward from (attn_out, x, seed).  d_attn_out, dx1 [rows, dim] (dx1 is the
  * gradient of the residual stream, i.e. of x); dparams [erv_block_mlp_params()] = dW_proj | db_proj |
  * dln_w | dln_b | dW_fc1 | db_fc1 | dW_fc2 | db_fc2; grad_accum (8 pointers, same order) as above. */
 int erv_block_mlp_params(void);
 size_t erv_block_mlp_bwd_workspace(int rows);
-int erv_block_mlp_bwd(const float* attn_out, const float* x, const float* dy, const float* const* params,
-                      float* d_attn_out, float* dx1, float* dparams, float* const* grad_accum, int rows, int dim,
-                      int mlp_dim, float eps, float p_drop, const long long* seed, int salt, void* workspace,
-                      size_t workspace_bytes, void* stream);
+int erv_block_mlp_bwd(const void* attn_out, int act_dtype, const float* x, const float* dy,
+                      const float* const* params, void* d_attn_out, float* dx1, float* dparams,
+                      float* const* grad_accum, int rows, int dim, int mlp_dim, float eps, float p_drop,
+                      const long long* seed, int salt, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the two ends of the ViT, model dim 32 ------------------------------------ */
 
