@@ -58,19 +58,33 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a, int phase, uint32_t 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(const ArArgs a) {
+__global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const ArArgs a) {
   const uint32_t ep = *a.epoch + 1;
   const int per = (a.n4 + kArCtas - 1) / kArCtas, beg = blockIdx.x * per, end = min(a.n4, beg + per);
   ar_barrier(a, 0, ep);  // every rank's gradient is complete
-  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  // all peer loads of two slice elements are issued before the first add: an NVLink round trip is ~2 us, and a load that is
+  // consumed right behind its issue would serialise `world` of them per element
+  for (int i = beg + threadIdx.x; i < end; i += 2 * blockDim.x) {
+    const int i2 = i + blockDim.x;
+    const bool two = i2 < end;
+    float4 v[2][kArMaxWorld];
 #pragma unroll
     for (int r = 0; r < kArMaxWorld; ++r)
-      if (r < a.world) {  // rank order: every rank computes bit-identical sums
-        const float4 v = ld_peer4(a.peer[r] + 4 * (size_t)i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      if (r < a.world) {
+        v[0][r] = ld_peer4(a.peer[r] + 4 * (size_t)i);
+        if (two) v[1][r] = ld_peer4(a.peer[r] + 4 * (size_t)i2);
       }
-    reinterpret_cast<float4*>(a.out)[i] = s;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (e == 1 && !two) break;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < kArMaxWorld; ++r)
+        if (r < a.world) {  // rank order: every rank computes bit-identical sums
+          s.x += v[e][r].x; s.y += v[e][r].y; s.z += v[e][r].z; s.w += v[e][r].w;
+        }
+      reinterpret_cast<float4*>(a.out)[e ? i2 : i] = s;
+    }
   }
   ar_barrier(a, 1, ep);  // every rank has read this slice of every buffer: the local one may now take the sums
   float* mine = a.peer[a.rank];
@@ -100,7 +114,7 @@ extern "C" int erv_allreduce_oneshot(const void* const* peer_bufs, size_t n, siz
     a.flags[r] = reinterpret_cast<uint32_t*>(a.peer[r] + flag_offset_floats);
   }
   a.out = scratch; a.epoch = epoch_dev; a.n4 = (int)(n / 4); a.rank = rank; a.world = world;
-  allreduce_oneshot_kernel<<<kArCtas, 1024, 0, (cudaStream_t)stream>>>(a);
+  allreduce_oneshot_kernel<<<kArCtas, 512, 0, (cudaStream_t)stream>>>(a);
   ERV_LAUNCH_CHECK();
   bump_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch_dev);
   ERV_LAUNCH_CHECK();

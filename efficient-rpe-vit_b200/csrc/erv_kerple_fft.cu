@@ -2,7 +2,7 @@
 // models/attention/favor_plus.py:221-260): D1 = C (phi_k (x) v), D2 = C phi_k by FFT along the patch axis, fused with the
 // read-out num = phi_q . D1, den = phi_q . D2, out = num / (den + 1e-6).  C[i][j] = exp(b[j - i]) is Toeplitz.
 //
-// Route for long sequences with many features (1024 < N - 1 <= 4096, M > 64), chosen per shape against the tensor-core tile route (erv_ktile_tc.cu)
+// Route for long sequences (2048 < N - 1 <= 4096; M > 64 or at least 16 (batch, head) pairs), chosen per shape against the tensor-core tile route (erv_ktile_tc.cu)
 // by measurement (profiles/r02_kerple_fft_vs_tile.md).  One 8192-point complex FFT lives entirely in the registers of a
 // 512-thread CTA (16 points per thread) and crosses shared memory twice:
 //
@@ -33,7 +33,7 @@ constexpr int NT = 512;        // threads per CTA: 16 points each
 constexpr int NP_MAX = 4096;   // patches per sequence this length serves
 constexpr int XROW = 33;       // padded row of the second exchange (32 points + 1)
 constexpr size_t kSmem = (size_t)256 * XROW * sizeof(float2);  // 67 584 B >= 8192 points
-constexpr size_t kSmemFwd = kSmem + 2 * (size_t)NP_MAX * sizeof(float2);  // + the phi_k / phi_q staging slots
+constexpr size_t kSmemFwd = kSmem + 2 * (size_t)NP_MAX * sizeof(float2) + (size_t)L * sizeof(float2);  // + phi_k / phi_q stages + G
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -158,8 +158,10 @@ struct FftArgs {
   const float* phi_q;   // [B*H][N][ld]
   const float* phi_k;
   const float2* coef;   // [H][L]: DFT of the circulant first column / L
+  const float2* phiT_q; // [B*H][ld/2][NPp]: patch rows of phi_q, feature-pair-major ((m, m+1) of one patch = one float2)
+  const float2* phiT_k;
   float* part;          // [chunks][B*H][DH+1][NP]: chunk partials of num (d < DH) and den (d = DH)
-  int B, N, H, DH, M, ld, NP, chunks, fp_per_chunk;
+  int B, N, H, DH, M, ld, NP, NPp, chunks, fp_per_chunk;
 };
 
 // G[h][k] = DFT(g)[k] / L, g[s] = c[-s] (s = 0..NP-1), g[L - s] = c[s] (s = 1..NP-1): y = g (*) x is y[i] = sum_j c[j - i] x[j]
@@ -183,6 +185,28 @@ __global__ void __launch_bounds__(NT, 1) kfft_coef_kernel(const float* __restric
   for (int q = 0; q < 16; ++q) coef[(size_t)h * L + t + 512 * q] = make_float2(x[q].x * (1.f / L), x[q].y * (1.f / L));
 }
 
+// phiT[plane][m / 2][i] = (phi[plane][i + 1][m], phi[plane][i + 1][m + 1]) for the patches i = 0..NP-1 (rows padded to NPp with
+// zeros): 32-token x 32-feature tiles through shared memory, coalesced on both sides.  plane = (q | k, batch*head).
+__global__ void __launch_bounds__(256) kfft_transpose_kernel(const float* __restrict__ phi, float2* __restrict__ phiT, int N, int ld,
+                                                             int NPp) {
+  __shared__ float tile[32][33];
+  const int plane = blockIdx.z, i0 = blockIdx.x * 32, m0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = phi + (size_t)plane * N * ld;
+  float2* dst = phiT + (size_t)plane * (ld / 2) * NPp;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r, m = m0 + tx;
+    tile[ty + 8 * r][tx] = (i < N - 1 && m < ld) ? src[(size_t)(i + 1) * ld + m] : 0.f;
+  }
+  __syncthreads();
+  // thread (ty, tx): feature pair m0/2 + ty + 8 r' (16 pairs per tile: two passes), token i0 + tx
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int fpl = ty + 8 * r, m = m0 + 2 * fpl, i = i0 + tx;
+    if (m < ld && i < NPp) dst[(size_t)(m / 2) * NPp + i] = make_float2(tile[tx][2 * fpl], tile[tx][2 * fpl + 1]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -192,8 +216,6 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
   const int b = pair / p.H, h = pair % p.H;
   const int N = p.N, NP = p.NP, ld = p.ld;
   const Twiddles w = make_twiddles();
-  const float* pq = p.phi_q + (size_t)pair * N * ld;
-  const float* pk = p.phi_k + (size_t)pair * N * ld;
   const float2* G = p.coef + (size_t)h * L;
 
   float vv[8], acc[8];
@@ -204,28 +226,32 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
     vv[r] = 0.f;
     if (i < NP) vv[r] = d < p.DH ? to_f(static_cast<const T*>(p.qkv)[qkv_off(b, i + 1, 2, h, N, p.H, p.DH) + d]) : 1.f;
   }
-  // phi_k[., m..m+1] of the next feature pair and phi_q[., m..m+1] of the current one are staged with 8-byte cp.async into
-  // per-thread slots of shared memory (thread t copies and later reads only elements t + 512 r), so the strided global
-  // reads are in flight under the two transforms instead of in front of them
+  // phi_k[., m..m+1] of the next feature pair and phi_q[., m..m+1] of the current one are staged with coalesced 16-byte
+  // cp.async from the feature-pair-major copies (kfft_transpose_kernel) while the transforms run; the filter coefficients of
+  // this head stay in shared memory for the whole CTA.  (First version: 8-byte strided copies straight from the token-major
+  // rows and 16 __ldg of G per transform -- 38 % of the warp-stall samples were long_scoreboard on exactly those two lines.)
   float2* stage_k = sm + 256 * XROW;
   float2* stage_q = stage_k + NP_MAX;
-  auto stage = [&](float2* dst, const float* src, int m) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int i = t + 512 * r;
-      if (i < NP)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)),
-                     "l"(src + (size_t)(i + 1) * ld + m) : "memory");
-    }
+  float2* Gs = stage_q + NP_MAX;
+  const int NPp = p.NPp;
+  auto stage = [&](float2* dst, const float2* src) {  // NPp float2 = NPp / 2 chunks of 16 bytes
+    for (int c = t; c < NPp / 2; c += NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 2 * c)),
+                   "l"(src + 2 * c) : "memory");
   };
   const int fp0 = chunk * p.fp_per_chunk, fp1 = min(fp0 + p.fp_per_chunk, (p.M + 1) / 2);
-  if (fp0 < fp1) stage(stage_k, pk, 2 * fp0);
+  const float2* tq = p.phiT_q + (size_t)pair * (ld / 2) * NPp;
+  const float2* tk = p.phiT_k + (size_t)pair * (ld / 2) * NPp;
+  for (int c = t; c < L / 2; c += NT)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(Gs + 2 * c)),
+                 "l"(G + 2 * c) : "memory");
+  if (fp0 < fp1) stage(stage_k, tk + (size_t)fp0 * NPp);
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   for (int fp = fp0; fp < fp1; ++fp) {
-    const int m = 2 * fp;
-    const bool two = m + 1 < p.M;
+    const bool two = 2 * fp + 1 < p.M;
     float2 x[16];
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();  // phi_k of this feature pair (and, the first time, G) copied by all threads
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;
@@ -235,17 +261,19 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
       x[r] = make_float2(vv[r] * f.x, vv[r] * f.y);
       x[r + 8] = make_float2(0.f, 0.f);
     }
-    if (fp + 1 < fp1) stage(stage_k, pk, m + 2);
-    stage(stage_q, pq, m);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
     fft8192(x, sm, w);
+    // every thread is past its stage_k / stage_q reads (the transform synchronises the CTA): refill both
+    if (fp + 1 < fp1) stage(stage_k, tk + (size_t)(fp + 1) * NPp);
+    stage(stage_q, tq + (size_t)fp * NPp);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const float2 y = cmul(x[q], __ldg(G + t + 512 * q));
+      const float2 y = cmul(x[q], Gs[t + 512 * q]);
       x[q] = make_float2(y.x, -y.y);  // inverse transform as conj(DFT(conj(.)))
     }
     fft8192(x, sm, w);
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();  // phi_q of this feature pair
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;
@@ -339,7 +367,7 @@ __global__ void __launch_bounds__(256) kfft_cls_kernel(const FftArgs p, const fl
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static std::atomic<int> g_fft_mode{-1};  // -1: environment default, 0 / 1: set by erv_kerple_set_fft()
-bool kerple_fft_eligible(int N, int DH, int M) {
+bool kerple_fft_eligible(int B, int N, int H, int DH, int M) {
   static const int env_mode = [] {
     const char* e = getenv("ERV_KERPLE_FFT");  // 0: never, 1: whenever the length fits, unset: measured crossover (below)
     return e ? atoi(e) : -1;
@@ -347,10 +375,10 @@ bool kerple_fft_eligible(int N, int DH, int M) {
   const int set = g_fft_mode.load(std::memory_order_relaxed), mode = set >= 0 ? set : env_mode;
   if (mode == 0) return false;
   const bool fits = N >= 3 && N - 1 <= kfft::NP_MAX && (DH == 8 || DH == 16 || DH == 32 || DH == 64);
-  // measured on B200 (profiles/r02_kerple_fft_vs_tile.md): at N = 4097 the FFT route is 2x faster than the tile route for
-  // M = 256 (253 vs 508 us per (batch, head)) and 1.2x slower for M = 44 (49.6 vs 40.5 us), where the tile route runs on
-  // tcgen05 (M <= 64); at N <= 1025 the tile route wins for every M
-  return mode == 1 ? fits : (fits && N - 1 > 1024 && M > 64);
+  // measured on B200, forward per (batch, head) pair (profiles/r02_kerple_fft_vs_tile.md): at N = 4097 the FFT route takes
+  // 156 us for M = 256 against 510 us on the tile route (CUDA cores for M > 64), and for M = 44 34.2 / 24.8 us at 16 / 64
+  // pairs against 40.8 / 35.8 us on the tcgen05 tiles; with 4 pairs (73 vs 53 us) and at N <= 2049 (27 vs 14 us) the tiles win
+  return mode == 1 ? fits : (fits && N - 1 > 2048 && (M > 64 || B * H >= 16));
 }
 
 static int kfft_chunks(int B, int H, int DH, int M, int* fp_per_chunk) {
@@ -362,11 +390,17 @@ static int kfft_chunks(int B, int H, int DH, int M, int* fp_per_chunk) {
   return (nfp + per - 1) / per;
 }
 
+static size_t kfft_ld(int M) { return (size_t)(M + 7) / 8 * 8; }  // kerple_ldphi (erv_tileattn.cu)
+static size_t kfft_npp(int N) { return (size_t)(N - 1 + 1) / 2 * 2; }
+static size_t kfft_phit_bytes(int B, int N, int H, int M) {  // phi_q and phi_k planes, feature-pair-major
+  return align_up((size_t)2 * B * H * (kfft_ld(M) / 2) * kfft_npp(N) * sizeof(float2), 256);
+}
+
 size_t kerple_fft_ws_bytes(int B, int N, int H, int DH, int M) {
   int per;
   const int chunks = kfft_chunks(B, H, DH, M, &per);
   return align_up((size_t)H * kfft::L * sizeof(float2), 256) +
-         align_up((size_t)chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256);
+         align_up((size_t)chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256) + kfft_phit_bytes(B, N, H, M);
 }
 
 template <typename T, int DH>
@@ -385,8 +419,13 @@ int kerple_fft_forward(const void* qkv, void* out, float* den, const float* phi_
   a.qkv = qkv; a.phi_q = phi_q; a.phi_k = phi_k;
   a.coef = reinterpret_cast<const float2*>(ws);
   a.part = reinterpret_cast<float*>((char*)ws + align_up((size_t)H * kfft::L * sizeof(float2), 256));
-  a.B = B; a.N = N; a.H = H; a.DH = DH; a.M = M; a.ld = ld; a.NP = N - 1;
+  a.B = B; a.N = N; a.H = H; a.DH = DH; a.M = M; a.ld = ld; a.NP = N - 1; a.NPp = (int)kfft_npp(N);
   a.chunks = kfft_chunks(B, H, DH, M, &a.fp_per_chunk);
+  ERV_CHECK_ARG((size_t)ld == kfft_ld(M) && phi_k == phi_q + (size_t)B * H * N * ld, "kerple_fft_forward: unexpected phi layout");
+  float2* phit = reinterpret_cast<float2*>((char*)a.part + align_up((size_t)a.chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256));
+  a.phiT_q = phit; a.phiT_k = phit + (size_t)B * H * (ld / 2) * a.NPp;
+  kfft::kfft_transpose_kernel<<<dim3((a.NPp + 31) / 32, (ld + 31) / 32, 2 * B * H), 256, 0, st>>>(phi_q, phit, N, ld, a.NPp);
+  ERV_LAUNCH_CHECK();
   ERV_CUDA(allow_smem(kfft::kfft_coef_kernel, kfft::kSmem));
   kfft::kfft_coef_kernel<<<H, kfft::NT, kfft::kSmem, st>>>(cexp, const_cast<float2*>(a.coef), N);
   ERV_LAUNCH_CHECK();

@@ -18,7 +18,7 @@ int launch_feature_map(const void* x, void* dx, size_t sb, size_t sh, size_t sn,
 int la_grid(int B, int H);
 int la_slots(int B, int H);
 // FFT route of the KERPLE forward for long sequences (erv_kerple_fft.cu)
-bool kerple_fft_eligible(int N, int DH, int M);
+bool kerple_fft_eligible(int B, int N, int H, int DH, int M);
 size_t kerple_fft_ws_bytes(int B, int N, int H, int DH, int M);
 int kerple_fft_forward(const void* qkv, void* out, float* den, const float* phi_q, const float* phi_k, int ld,
                        const float* cexp, void* ws, int B, int N, int H, int DH, int M, int dtype, cudaStream_t st);
@@ -907,7 +907,7 @@ static KerpleWs kerple_ws(int B, int N, int H, int DH, int M, int backward) {
   w.phi = o; o += phi;
   w.dphi = o; if (backward) o += phi;
   w.dpart = o; if (backward) o += align_up((size_t)B * H * ((N + TQ - 1) / TQ) * (2 * N - 1) * sizeof(float), 256);
-  w.fft = o; if (!backward && kerple_fft_eligible(N, DH, M)) o += kerple_fft_ws_bytes(B, N, H, DH, M);
+  w.fft = o; if (!backward && kerple_fft_eligible(B, N, H, DH, M)) o += kerple_fft_ws_bytes(B, N, H, DH, M);
   w.total = o;
   return w;
 }
@@ -956,7 +956,7 @@ extern "C" int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_o
   if (workspace_bytes < w.total) { set_error("%s: workspace too small", fn); return ERV_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  if (kerple_fft_eligible(N, head_dim, M)) {  // long sequences: the reference's FFT route, fused with the read-out
+  if (kerple_fft_eligible(B, N, H, head_dim, M)) {  // long sequences: the reference's FFT route, fused with the read-out
     rc = kerple_features(qkv, ws, w, omega, rel_pos_bias, B, N, H, head_dim, M, kind, dtype, st);
     if (rc) return rc;
     const int ld = (int)kerple_ldphi(M);

@@ -35,9 +35,11 @@ class UnifiedTransformerBlock(nn.Module):
         self.norm1 = LayerNorm(dim)
         self.norm2 = LayerNorm(dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, drop_seed=None, drop_salt: int = 0) -> torch.Tensor:
+        """drop_seed / drop_salt (optional, fused path only): a device-resident dropout seed shared by the caller's blocks and
+        this block's index, so that a model draws ONE seed per forward pass instead of one per block (BaseViT.features)."""
         if self._fused(x):
-            return self._forward_fused(x)
+            return self._forward_fused(x, drop_seed, drop_salt)
         x = x + self.attention(self.norm1(x), rpe=self.rpe)  # the RPE goes INTO the attention
         return x + self.mlp(self.norm2(x))
 
@@ -53,7 +55,7 @@ class UnifiedTransformerBlock(nn.Module):
         # p >= 1 (nn.Dropout accepts 1.0: everything dropped) has no finite 1/(1-p): leave it to the op-by-op modules
         return att.proj_dropout.p == self.mlp[2].p == self.mlp[4].p and att.proj_dropout.p < 1.0
 
-    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+    def _forward_fused(self, x: torch.Tensor, drop_seed=None, drop_salt: int = 0) -> torch.Tensor:
         att = self.attention
         att.before_qkv(x.shape, self.rpe)
         # bf16 autocast: the attention core sees the bf16 qkv an autocast Linear would hand it (written directly by the
@@ -62,9 +64,9 @@ class UnifiedTransformerBlock(nn.Module):
                                   with_residual=True, out_dtype=torch.bfloat16 if torch.is_autocast_enabled() else None)
         a = att.core(qkv, x.shape, self.rpe)
         p = self.mlp[2].p if self.training else 0.0
-        seed = ops.dropout_seed(x.device) if p > 0 else None
+        seed = (drop_seed if drop_seed is not None else ops.dropout_seed(x.device)) if p > 0 else None
         return ops.block_mlp(a, x, att.proj.weight, att.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp[0].weight,
-                             self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias, self.norm2.eps, p, seed)
+                             self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias, self.norm2.eps, p, seed, drop_salt)
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}, mlp_dim={self.mlp_dim}, has_rpe={self.rpe is not None}"
@@ -140,8 +142,14 @@ class BaseViT(nn.Module):
             x = self.patch_embedding(self.patchify(x))
             x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embedding
         cut = getattr(self, "_cut_after", None)
+        # one device-resident dropout seed per forward pass; block i salts it with its index (the mask hash takes
+        # (seed, salt, element)), instead of a clone + add kernel pair per block
+        seed = None
+        if self.training and x.is_cuda and any(getattr(b, "mlp", None) is not None and b.mlp[2].p > 0
+                                                for b in self.transformer_blocks):
+            seed = ops.dropout_seed(x.device)
         for i, block in enumerate(self.transformer_blocks):
-            x = block(x)
+            x = block(x, seed, 0x1000 + i) if seed is not None else block(x)
             if cut == i and x.requires_grad:  # erv_b200.train: the backward is split here to overlap the gradient all-reduce
                 self._cut_tensor = x
         return x

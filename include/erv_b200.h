@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ERV_ABI_VERSION 1
+#define ERV_ABI_VERSION 2  /* 2: activation dtype in the erv_block_* calls, erv_kerple_set_fft */
 
 enum { ERV_OK = 0, ERV_E_INVALID = 1, ERV_E_UNSUPPORTED = 2, ERV_E_CUDA = 3, ERV_E_WORKSPACE = 4 };
 enum { ERV_F32 = 0, ERV_BF16 = 1 };
@@ -191,8 +191,8 @@ int erv_kerple_attention_fwd(const void* qkv, void* out, float* den_out, const f
                              int kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 /* Route of erv_kerple_attention_fwd: 1 = the reference's FFT route (kerple.py:252-270 -> fft_utils.py:142-170: Toeplitz
  * product by FFT along the patch axis, here a shared-memory radix-16 transform of 8192 points fused with the phi(q)
- * read-out) whenever N - 1 <= 4096, 0 = Toeplitz-masked tiles always, -1 = default (FFT for N - 1 > 1024 and M > 64, the measured
- * crossover, or the ERV_KERPLE_FFT environment variable).  Both routes compute the same function; the workspace query follows the mode. */
+ * read-out) whenever N - 1 <= 4096, 0 = Toeplitz-masked tiles always, -1 = default (FFT for N - 1 > 2048 and (M > 64 or B*H >= 16),
+ * the measured crossover, or the ERV_KERPLE_FFT environment variable).  Both routes compute the same function; the workspace query follows the mode. */
 void erv_kerple_set_fft(int mode);
 int erv_kerple_attention_bwd(const void* qkv, const void* out, const float* den, const void* dout,
                              void* dqkv, float* dbias, const float* omega, const float* rel_pos_bias,

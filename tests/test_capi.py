@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in erv_b200.h but not exported"
         assert n in _capi.SIGNATURES, f"{n} has no ctypes signature"
     assert set(_capi.SIGNATURES) == set(names)
-    assert lib.erv_abi_version() == 1
+    assert lib.erv_abi_version() == 2
 
 
 def test_status_to_exception_mapping():
