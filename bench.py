@@ -19,6 +19,7 @@ tools/install_reference.py: create_model + torch.optim.Adam + CrossEntropy, expe
 on the host cores at the GPU arm's batch; the oracle port is used only when baseline/_ref is absent (`kind` says which).
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -69,9 +70,10 @@ class ClockSampler(threading.Thread):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.sm, self.reasons, self.sm_max, self.proc = index, [], set(), None, None
+        self.period = period  # NVML calls serialise on a driver lock shared by all ranks: poll more slowly when there are several
         self._stop_evt = threading.Event()
         self._nvml = None
         try:
@@ -96,7 +98,7 @@ class ClockSampler(threading.Thread):
                 self.reasons.update(k for k, b in bits.items() if r & b)
             except Exception:
                 pass
-            self._stop_evt.wait(0.005)
+            self._stop_evt.wait(self.period)
 
     def _poll_smi(self):
         try:
@@ -119,13 +121,19 @@ class ClockSampler(threading.Thread):
         else:
             self._poll_smi()
 
+    def mark(self):
+        """Start of the timed region: samples and throttle reasons seen before this call are dropped."""
+        self._mark = len(self.sm)
+        self.reasons.clear()
+
     def stop(self):
         self._stop_evt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        sm = self.sm[getattr(self, "_mark", 0):] or self.sm
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
@@ -284,9 +292,14 @@ def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
     # ---- value: inputs resident in HBM ------------------------------------------------------------------
     for i in range(warmup):
         trainer.step(*pool[i % pool_n])
-    barrier()
-    sampler = ClockSampler(local)
+    # the NVML sampler is created and started BEFORE the barrier: nvmlInit takes a different number of milliseconds on every
+    # rank, and a rank that enters the timed loop late makes all the others wait for it inside their first all-reduce
+    sampler = ClockSampler(local, 0.005 if world == 1 else 0.02)
     sampler.start()
+    gc.collect()
+    gc.disable()  # no collector pause on one rank while the others wait in a collective
+    barrier()
+    sampler.mark()
     _capi.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -296,6 +309,7 @@ def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
+    gc.enable()
     eager_launches = _capi.launch_count()
     per_step = trainer.kernels_per_step()
     res = {"ms_per_step": ms_total / steps, "value": world * B * steps / (ms_total / 1e3), "clocks": clocks,

@@ -390,7 +390,7 @@ def test_kerple_fft_route_matches_reference(fname, kerple_fft_forced):
     ("relu", 1, 1030, 32, 2, 33),         # odd feature count: the last transform carries one real column
     ("favor_plus", 1, 600, 64, 2, 16),    # head_dim 32
     ("favor_plus", 1, 4097, 32, 2, 44),   # config 5: all 4096 patches, circular length exactly 2*4096
-    ("relu", 3, 2050, 32, 2, 256),        # M = 256, default dispatch (N - 1 > 1024)
+    ("relu", 3, 2050, 32, 2, 256),        # M = 256, three batches, 2049 patches
 ])
 def test_kerple_fft_route_matches_oracle(a, b, n, dim, heads, m, kerple_fft_forced):
     from erv_b200 import ATTENTION_REGISTRY, RPE_REGISTRY
