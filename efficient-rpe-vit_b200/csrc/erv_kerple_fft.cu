@@ -31,6 +31,7 @@ namespace kfft {
 constexpr int L = 8192;        // transform length
 constexpr int NT = 512;        // threads per CTA: 16 points each
 constexpr int NP_MAX = 4096;   // patches per sequence this length serves
+constexpr int kClsSeg = 32;    // CTAs per (batch, head) pair that share the CLS row
 constexpr int XROW = 33;       // padded row of the second exchange (32 points + 1)
 constexpr size_t kSmem = (size_t)256 * XROW * sizeof(float2);  // 67 584 B >= 8192 points
 constexpr size_t kSmemFwd = kSmem + 2 * (size_t)NP_MAX * sizeof(float2) + (size_t)L * sizeof(float2);  // + phi_k / phi_q stages + G
@@ -161,6 +162,7 @@ struct FftArgs {
   const float2* phiT_q; // [B*H][ld/2][NPp]: patch rows of phi_q, feature-pair-major ((m, m+1) of one patch = one float2)
   const float2* phiT_k;
   float* part;          // [chunks][B*H][DH+1][NP]: chunk partials of num (d < DH) and den (d = DH)
+  float* cls_part;      // [B*H][kClsSeg][DH+1]: partial sums of the CLS row
   int B, N, H, DH, M, ld, NP, NPp, chunks, fp_per_chunk;
 };
 
@@ -293,30 +295,39 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
   }
 }
 
-// patches i >= 1: sum the chunk partials in a fixed order, add the CLS column c[-i] (phi_q[i] . phi_k[0]) [v_0 | 1], divide
+// patches i >= 1: sum the chunk partials in a fixed order, add the CLS column c[-i] (phi_q[i] . phi_k[0]) [v_0 | 1], divide;
+// i = 0 (CLS row): sum the kClsSeg partials of kfft_cls_kernel in a fixed order, divide
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) kfft_finalize_kernel(const FftArgs p, const float* __restrict__ cexp, T* __restrict__ out,
                                                             float* __restrict__ den_out) {
-  const int pair = blockIdx.y, i = 1 + blockIdx.x * 128 + threadIdx.x;
+  const int pair = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
   const int b = pair / p.H, h = pair % p.H, N = p.N, NP = p.NP;
   if (i >= N) return;
   float nd[DH + 1];
 #pragma unroll
   for (int d = 0; d <= DH; ++d) nd[d] = 0.f;
-  for (int c = 0; c < p.chunks; ++c) {
-    const float* src = p.part + (((size_t)c * p.B * p.H + pair) * (DH + 1)) * NP + (i - 1);
+  if (i == 0) {
+    for (int sgm = 0; sgm < kClsSeg; ++sgm) {
+      const float* src = p.cls_part + ((size_t)pair * kClsSeg + sgm) * (DH + 1);
 #pragma unroll
-    for (int d = 0; d <= DH; ++d) nd[d] += src[(size_t)d * NP];
+      for (int d = 0; d <= DH; ++d) nd[d] += src[d];
+    }
+  } else {
+    for (int c = 0; c < p.chunks; ++c) {
+      const float* src = p.part + (((size_t)c * p.B * p.H + pair) * (DH + 1)) * NP + (i - 1);
+#pragma unroll
+      for (int d = 0; d <= DH; ++d) nd[d] += src[(size_t)d * NP];
+    }
+    const float* q = p.phi_q + ((size_t)pair * N + i) * p.ld;
+    const float* k0 = p.phi_k + (size_t)pair * N * p.ld;
+    float s = 0.f;
+    for (int m = 0; m < p.M; ++m) s = fmaf(q[m], __ldg(k0 + m), s);
+    s *= __ldg(cexp + (size_t)h * (2 * N - 1) + (N - 1) - i);  // c[0 - i]
+    const T* v0 = static_cast<const T*>(p.qkv) + qkv_off(b, 0, 2, h, N, p.H, DH);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) nd[d] = fmaf(s, to_f(v0[d]), nd[d]);
+    nd[DH] += s;
   }
-  const float* q = p.phi_q + ((size_t)pair * N + i) * p.ld;
-  const float* k0 = p.phi_k + (size_t)pair * N * p.ld;
-  float s = 0.f;
-  for (int m = 0; m < p.M; ++m) s = fmaf(q[m], __ldg(k0 + m), s);
-  s *= __ldg(cexp + (size_t)h * (2 * N - 1) + (N - 1) - i);  // c[0 - i]
-  const T* v0 = static_cast<const T*>(p.qkv) + qkv_off(b, 0, 2, h, N, p.H, DH);
-#pragma unroll
-  for (int d = 0; d < DH; ++d) nd[d] = fmaf(s, to_f(v0[d]), nd[d]);
-  nd[DH] += s;
   const float inv = 1.f / (nd[DH] + kEps);
   T* o = out + out_off(b, i, h, N, p.H, DH);
 #pragma unroll
@@ -324,26 +335,34 @@ __global__ void __launch_bounds__(128) kfft_finalize_kernel(const FftArgs p, con
   den_out[(size_t)pair * N + i] = nd[DH];
 }
 
-// CLS row: num[0] = sum_j c[j] (phi_q[0] . phi_k[j]) [v_j | 1] — one CTA per (batch, head), deterministic tree sums
+// CLS row: num[0] = sum_j c[j] (phi_q[0] . phi_k[j]) [v_j | 1].  kClsSeg CTAs per (batch, head), each a strided share of the
+// keys; deterministic tree sums, the kClsSeg partials are combined by kfft_finalize_kernel.  (One CTA per pair took 98 us.)
 template <typename T, int DH>
-__global__ void __launch_bounds__(256) kfft_cls_kernel(const FftArgs p, const float* __restrict__ cexp, T* __restrict__ out,
-                                                       float* __restrict__ den_out) {
+__global__ void __launch_bounds__(256) kfft_cls_kernel(const FftArgs p, const float* __restrict__ cexp) {
   __shared__ float q0[320];
   __shared__ float red[8][DH + 1];
-  const int pair = blockIdx.x, b = pair / p.H, h = pair % p.H, N = p.N, t = threadIdx.x;
-  for (int m = t; m < p.M; m += 256) q0[m] = p.phi_q[(size_t)pair * N * p.ld + m];
+  const int sgm = blockIdx.x, pair = blockIdx.y, b = pair / p.H, h = pair % p.H, N = p.N, t = threadIdx.x;
+  for (int m = t; m < p.ld; m += 256) q0[m] = m < p.M ? p.phi_q[(size_t)pair * N * p.ld + m] : 0.f;
   __syncthreads();
   float nd[DH + 1];
 #pragma unroll
   for (int d = 0; d <= DH; ++d) nd[d] = 0.f;
-  for (int j = t; j < N; j += 256) {
+  for (int j = sgm * 256 + t; j < N; j += kClsSeg * 256) {
     const float* k = p.phi_k + ((size_t)pair * N + j) * p.ld;
-    float s = 0.f;
-    for (int m = 0; m < p.M; ++m) s = fmaf(q0[m], k[m], s);
-    s *= __ldg(cexp + (size_t)h * (2 * N - 1) + (N - 1) + j);  // c[j - 0]
+    float s0 = 0.f, s1 = 0.f;
+    for (int m = 0; m < p.ld; m += 4) {  // ld is a multiple of 8; columns >= M are masked on both sides
+      const float4 kv = ld4(k + m);
+      s0 = fmaf(q0[m], m < p.M ? kv.x : 0.f, s0); s1 = fmaf(q0[m + 1], m + 1 < p.M ? kv.y : 0.f, s1);
+      s0 = fmaf(q0[m + 2], m + 2 < p.M ? kv.z : 0.f, s0); s1 = fmaf(q0[m + 3], m + 3 < p.M ? kv.w : 0.f, s1);
+    }
+    const float s = (s0 + s1) * __ldg(cexp + (size_t)h * (2 * N - 1) + (N - 1) + j);  // c[j - 0]
     const T* v = static_cast<const T*>(p.qkv) + qkv_off(b, j, 2, h, N, p.H, DH);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) nd[d] = fmaf(s, to_f(v[d]), nd[d]);
+    for (int d = 0; d < DH; d += 4) {
+      const float4 vv = ld4(v + d);
+      nd[d] = fmaf(s, vv.x, nd[d]); nd[d + 1] = fmaf(s, vv.y, nd[d + 1]);
+      nd[d + 2] = fmaf(s, vv.z, nd[d + 2]); nd[d + 3] = fmaf(s, vv.w, nd[d + 3]);
+    }
     nd[DH] += s;
   }
 #pragma unroll
@@ -356,11 +375,8 @@ __global__ void __launch_bounds__(256) kfft_cls_kernel(const FftArgs p, const fl
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) s += red[wv][t];
-    red[0][t] = s;
+    p.cls_part[((size_t)pair * kClsSeg + sgm) * (DH + 1) + t] = s;
   }
-  __syncthreads();
-  if (t < DH) put(out + out_off(b, 0, h, N, p.H, DH) + t, red[0][t] / (red[0][DH] + kEps));
-  if (t == DH) den_out[(size_t)pair * N] = red[0][DH];
 }
 
 }  // namespace kfft
@@ -395,19 +411,21 @@ static size_t kfft_npp(int N) { return (size_t)(N - 1 + 1) / 2 * 2; }
 static size_t kfft_phit_bytes(int B, int N, int H, int M) {  // phi_q and phi_k planes, feature-pair-major
   return align_up((size_t)2 * B * H * (kfft_ld(M) / 2) * kfft_npp(N) * sizeof(float2), 256);
 }
+static size_t kfft_cls_bytes(int B, int H, int DH) { return align_up((size_t)B * H * kfft::kClsSeg * (DH + 1) * sizeof(float), 256); }
 
 size_t kerple_fft_ws_bytes(int B, int N, int H, int DH, int M) {
   int per;
   const int chunks = kfft_chunks(B, H, DH, M, &per);
   return align_up((size_t)H * kfft::L * sizeof(float2), 256) +
-         align_up((size_t)chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256) + kfft_phit_bytes(B, N, H, M);
+         align_up((size_t)chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256) + kfft_phit_bytes(B, N, H, M) +
+         kfft_cls_bytes(B, H, DH);
 }
 
 template <typename T, int DH>
 static int kfft_tail(const kfft::FftArgs& a, const float* cexp, void* out, float* den, cudaStream_t st) {
-  kfft::kfft_finalize_kernel<T, DH><<<dim3((a.NP + 127) / 128, a.B * a.H), 128, 0, st>>>(a, cexp, static_cast<T*>(out), den);
+  kfft::kfft_cls_kernel<T, DH><<<dim3(kfft::kClsSeg, a.B * a.H), 256, 0, st>>>(a, cexp);
   ERV_LAUNCH_CHECK();
-  kfft::kfft_cls_kernel<T, DH><<<a.B * a.H, 256, 0, st>>>(a, cexp, static_cast<T*>(out), den);
+  kfft::kfft_finalize_kernel<T, DH><<<dim3((a.N + 127) / 128, a.B * a.H), 128, 0, st>>>(a, cexp, static_cast<T*>(out), den);
   ERV_LAUNCH_CHECK();
   return ERV_OK;
 }
@@ -424,6 +442,7 @@ int kerple_fft_forward(const void* qkv, void* out, float* den, const float* phi_
   ERV_CHECK_ARG((size_t)ld == kfft_ld(M) && phi_k == phi_q + (size_t)B * H * N * ld, "kerple_fft_forward: unexpected phi layout");
   float2* phit = reinterpret_cast<float2*>((char*)a.part + align_up((size_t)a.chunks * B * H * (DH + 1) * (N - 1) * sizeof(float), 256));
   a.phiT_q = phit; a.phiT_k = phit + (size_t)B * H * (ld / 2) * a.NPp;
+  a.cls_part = reinterpret_cast<float*>((char*)phit + kfft_phit_bytes(B, N, H, M));
   kfft::kfft_transpose_kernel<<<dim3((a.NPp + 31) / 32, (ld + 31) / 32, 2 * B * H), 256, 0, st>>>(phi_q, phit, N, ld, a.NPp);
   ERV_LAUNCH_CHECK();
   ERV_CUDA(allow_smem(kfft::kfft_coef_kernel, kfft::kSmem));
