@@ -82,10 +82,11 @@ constexpr float kStLog2e = 1.4426950408889634f;
 template <typename T>
 __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) {
   constexpr int DH = 16;
-  constexpr uint32_t COL_S = 0, COL_O = 128;
+  constexpr uint32_t COL_S = 0, COL_O = 256;  // S of up to two key tiles at [0,128) and [128,256), O behind them
   __shared__ __align__(128) uint8_t qi[2 * XD_BYTES];
   __shared__ __align__(128) uint8_t ki[2 * XD_BYTES];
   __shared__ __align__(128) uint8_t vi[6 * VI_CH];
+  __shared__ __align__(128) uint8_t vi2[6 * VI_CH];  // value image of the second key tile (single-pass path)
   __shared__ float ml_s[4][128][2];
   __shared__ __align__(8) uint64_t bar_s, bar_pv;
   __shared__ uint32_t tmem_base_s;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
   const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
   const uint64_t seed = p.dropout_p > 0.f ? st_seed(p) : 0ull;
 
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     mbar_init(&bar_s, 1);
     mbar_init(&bar_pv, 1);
@@ -126,9 +127,9 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
     if (quarter == 0) st_rotated_row<T>(qi, qb, tok_stride, g.t0, g.rows, row, r_n, p, h);
 
     // scores of this thread's 32 columns in log2 units (masked entries -inf): S (TMEM) -> sc[]
-    auto load_scores = [&](float (&sc)[32], int w0, int rows_w) {
+    auto load_scores = [&](float (&sc)[32], int w0, int rows_w, uint32_t scol = 0) {
       uint32_t sv[32];
-      tmem_ld32_nowait(tm + lane_off + COL_S + 32 * quarter, sv);
+      tmem_ld32_nowait(tm + lane_off + COL_S + scol + 32 * quarter, sv);
       tmem_wait_ld();
       const int c0 = 32 * quarter;
       int cp = 0, cn = 0;
@@ -149,11 +150,11 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
         sc[i] = ok ? __uint_as_float(sv[i]) * sl2 : -INFINITY;
       }
     };
-    auto issue_scores = [&]() {
+    auto issue_scores = [&](uint32_t scol = 0) {
       if (warp == 0 && elect_one()) {
         fence_after_sync();
         for (int term = 0; term < 3; ++term)
-          mma_f16(tm + COL_S, make_desc(smem_u32(qi + (term == 2 ? XD_BYTES : 0)), 128, XD_SBO),
+          mma_f16(tm + COL_S + scol, make_desc(smem_u32(qi + (term == 2 ? XD_BYTES : 0)), 128, XD_SBO),
                   make_desc(smem_u32(ki + (term == 1 ? XD_BYTES : 0)), 128, XD_SBO), idesc_s, term > 0);
         commit(&bar_s);
       }
@@ -167,13 +168,14 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
         st_rotated_row<T>(ki, kb, tok_stride, tw0, rows_w, row, packed ? row - wp * N : w0 + row, p, h);
       }
     };
-    auto value_rows = [&](int tw0, int rows_w) {
+    auto value_rows = [&](int tw0, int rows_w, uint8_t* img = nullptr) {
+      if (img == nullptr) img = vi;
       if (quarter == 2) {
         float v[DH];
 #pragma unroll
         for (int a = 0; a < DH; ++a) v[a] = 0.f;
         if (row < rows_w) load_row<T, DH>(vb + (size_t)(tw0 + row) * tok_stride, v);
-        kt_store_row_mnmajor(vi, row, v, 0.f);
+        kt_store_row_mnmajor(img, row, v, 0.f);
       }
     };
     // combine the four threads of a row: log-sum-exp in log2 units (-inf for a fully masked row)
@@ -246,8 +248,101 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
       }
     };
 
+    // unnormalised weights e = exp(s - M) of one key tile (dropout applied), written back over its S columns as bf16 hi / lo;
+    // returns the thread's share of the row sum (before dropout)
+    auto weights_unnormalised = [&](float (&sc)[32], float M, int w0, uint32_t scol) -> float {
+      const int c0 = 32 * quarter;
+      uint32_t hw[16], lw[16];
+      int cp = 0, cn = 0;
+      if (packed) { cp = c0 / N; cn = c0 - cp * N; }
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float a[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int j;
+          if (packed) {
+            j = cn;
+            if (++cn == N) { cn = 0; ++cp; }
+          } else {
+            j = w0 + c0 + i + e;
+          }
+          float pv = (sc[i + e] > -INFINITY) ? ex2_approx(sc[i + e] - M) : 0.f;
+          l += pv;
+          if (p.dropout_p > 0.f && pv != 0.f)
+            pv = (st_uniform(seed, pair, (uint32_t)r_n, (uint32_t)j) >= p.dropout_p) ? pv * keep_scale : 0.f;
+          a[e] = pv;
+        }
+        split_pack2(a[0], a[1], hw[i >> 1], lw[i >> 1]);
+      }
+      const uint32_t cbase = tm + lane_off + COL_S + scol + c0;
+      uint32_t w8[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w8[i] = hw[8 * q + i];
+        tmem_st8(cbase + 8 * q, w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w8[i] = lw[8 * q + i];
+        tmem_st8(cbase + 16 + 8 * q, w8);
+      }
+      return l;
+    };
+
     float lse2;
-    if (g.nwalk == 1) {  // one key tile: statistics and weights from the same registers
+    float o_scale = 1.f;
+    if (g.nwalk <= 2 && p.attn_out == nullptr) {
+      // Single pass for up to two key tiles (N <= 256): both score tiles stay in tensor memory, the row maximum is exchanged
+      // first, then ONE exponential per score gives the unnormalised weight e = exp(s - M) and the row sum; O = (e v) / L is
+      // scaled in the epilogue.  (The two-sweep path below evaluates every exponential twice and, for two key tiles, every
+      // score product twice.)  Not used with return_attention, which needs normalised weights.
+      float m_t = -INFINITY;
+      for (int wi = 0; wi < g.nwalk; ++wi) {
+        const int w0 = wi * KT, rows_w = g.nwalk == 1 ? g.rows : min(KT, N - w0);
+        key_rows(g.wbase + w0, rows_w, w0);
+        value_rows(g.wbase + w0, rows_w, wi ? vi2 : vi);
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+        issue_scores(128u * wi);  // returns when the product has completed: the key image may be overwritten
+        float sc[32];
+        load_scores(sc, w0, rows_w, 128u * wi);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m_t = fmaxf(m_t, sc[i]);
+      }
+      ml_s[quarter][row][0] = m_t;
+      __syncthreads();
+      const float M = fmaxf(fmaxf(ml_s[0][row][0], ml_s[1][row][0]), fmaxf(ml_s[2][row][0], ml_s[3][row][0]));
+      float l_t = 0.f;
+      for (int wi = 0; wi < g.nwalk; ++wi) {
+        const int w0 = wi * KT, rows_w = g.nwalk == 1 ? g.rows : min(KT, N - w0);
+        float sc[32];
+        load_scores(sc, w0, rows_w, 128u * wi);
+        l_t += weights_unnormalised(sc, M, w0, 128u * wi);
+      }
+      tmem_wait_st();
+      ml_s[quarter][row][1] = l_t;
+      fence_before_sync();
+      __syncthreads();
+      if (warp == 0 && elect_one()) {
+        fence_after_sync();
+        for (int wi = 0; wi < g.nwalk; ++wi) {
+          const int rows_w = g.nwalk == 1 ? g.rows : min(KT, N - wi * KT);
+          const int ksteps = (rows_w + 15) >> 4;
+          for (int t = 0; t < ksteps; ++t) {
+            const uint32_t ca = tm + COL_S + 128u * wi + 32 * (t >> 1) + 8 * (t & 1);
+            const uint64_t bd = make_desc(smem_u32(wi ? vi2 : vi) + (uint32_t)t * 256, 128, VI_CH);
+            mma_f16_ts(tm + COL_O, ca, bd, idesc_pv_a, wi > 0 || t > 0);
+            mma_f16_ts(tm + COL_O, ca + 16, bd, idesc_pv_b, true);
+          }
+        }
+        commit(&bar_pv);
+      }
+      const float L = (ml_s[0][row][1] + ml_s[1][row][1]) + (ml_s[2][row][1] + ml_s[3][row][1]);
+      lse2 = (M > -INFINITY && L > 0.f) ? M + log2f(L) : -INFINITY;
+      o_scale = L > 0.f ? 1.f / L : 0.f;
+    } else if (g.nwalk == 1) {  // one key tile: statistics and weights from the same registers
       key_rows(g.wbase, g.rows, 0);
       value_rows(g.wbase, g.rows);
       fence_smem_to_async();
@@ -319,15 +414,15 @@ __global__ void __launch_bounds__(KTHREADS, 1) stile_fwd_kernel(const StArgs p) 
         T* ob = static_cast<T*>(p.out) + ((size_t)(g.t0 + row) * H + h) * DH;
 #pragma unroll
         for (int cc = 0; cc < DH / 4; ++cc)
-          st4(ob + 4 * cc, make_float4(o0[4 * cc] + o1[4 * cc], o0[4 * cc + 1] + o1[4 * cc + 1], o0[4 * cc + 2] + o1[4 * cc + 2],
-                                       o0[4 * cc + 3] + o1[4 * cc + 3]));
+          st4(ob + 4 * cc, make_float4((o0[4 * cc] + o1[4 * cc]) * o_scale, (o0[4 * cc + 1] + o1[4 * cc + 1]) * o_scale,
+                                       (o0[4 * cc + 2] + o1[4 * cc + 2]) * o_scale, (o0[4 * cc + 3] + o1[4 * cc + 3]) * o_scale));
         p.lse[((size_t)r_b * H + h) * N + r_n] = lse2 * 0.6931471805599453f;  // natural log, as the reference's logsumexp
       }
     }
     fence_before_sync();
     __syncthreads();  // images, statistics and TMEM columns are reused by the next tile
   }
-  if (warp == 0) tmem_dealloc(tm, 256);
+  if (warp == 0) tmem_dealloc(tm, 512);
 }
 
 // ---- backward --------------------------------------------------------------------------------------------------
