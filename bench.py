@@ -318,30 +318,44 @@ def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
            "dtype": "bf16" if autocast is not None else "f32", "tokens": (w["image"] // w["patch"]) ** 2 + 1}
 
     # ---- e2e: host buffers in, loss out, every step ------------------------------------------------------
-    # Every step's batch starts in pinned host memory and its loss is read back on the host; the copy of batch i+1 is
-    # issued (side stream, double-buffered staging) before the host waits for the loss of batch i, as a data loader
-    # with pin_memory / non_blocking copies does.  The K-step loop is repeated until it has run for >= 0.5 s.
+    # Every step's batch starts in pinned host memory and every step's loss is read back on the host.  The copy of batch
+    # i+1 is issued on a side stream (double-buffered staging) as a data loader with pin_memory / non_blocking copies does;
+    # the loss of step i is copied to pinned memory right behind the step and read by the host while step i+1 runs (one
+    # step behind, like an asynchronous logger), so the GPU does not idle for a host round trip between steps.  The K-step
+    # loop is repeated until it has run for >= 0.5 s.
     if do_e2e:
         host_pool = [(i.cpu().pin_memory(), l.cpu().pin_memory()) for i, l in pool[:min(pool_n, 8)]]
-        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
         for i in range(2):
             trainer.step(*host_pool[i % len(host_pool)])
         reps = max(1, int(0.5 / max(1e-6, ms_total / 1e3)) + 1)
         n_e2e = steps * reps
+        gc.collect()
+        gc.disable()
         barrier()
         t0 = time.perf_counter()
         trainer.prefetch(*host_pool[0])
+        seen = 0.0
         for i in range(n_e2e):
             l = trainer.step_prefetched()
+            loss_host[i % 2].copy_(l, non_blocking=True)  # device -> pinned host, right behind the step
+            loss_ready[i % 2].record()
             if i + 1 < n_e2e:
                 trainer.prefetch(*host_pool[(i + 1) % len(host_pool)])
-            loss_host.copy_(l, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+            if i > 0:  # the caller reads EVERY step's loss; the read of step i-1 happens while step i runs (an asynchronous logger)
+                loss_ready[(i - 1) % 2].synchronize()
+                seen += float(loss_host[(i - 1) % 2])
+        loss_ready[(n_e2e - 1) % 2].synchronize()
+        seen += float(loss_host[(n_e2e - 1) % 2])
+        torch.cuda.current_stream().synchronize()
+        gc.enable()
+        assert seen == seen, "e2e loop read a NaN loss"
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         res["e2e"] = {"value": world * B * n_e2e / e2e_s, "unit": "images/s",
                       "h2d_bytes_per_step": world * (img_bytes + B * 8), "d2h_bytes_per_step": world * 4,
-                      "steps_timed": n_e2e}
+                      "steps_timed": n_e2e, "loss_read": "every step, by the host, one step behind (pinned copy + event)"}
 
     # ---- roofline: dominant attention kernel, CUDA events around its launches (separate eager pass) --------
     ops.PROFILE = {}
