@@ -450,15 +450,20 @@ int la_tc2_backward(const void* qkv, const void* out, const void* dout, void* dq
                     int H, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
                     int dtype, const float* state, cudaStream_t st);
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
-                  const float* ta, const float* tb, int dtype, cudaStream_t st);
+                  const float* ta, const float* tb, int dtype, float* state, cudaStream_t st);
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                    int H, int DH, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
-                   int dtype, cudaStream_t st);
+                   int dtype, const float* state, cudaStream_t st);
 }  // namespace erv
 
 // Floats of the [S|z] state the forward saves for the backward (0: these shapes recompute S in the backward).
 extern "C" size_t erv_linear_attention_state_floats(int B, int N, int H, int head_dim, int M) {
-  if (B <= 0 || H <= 0 || !erv::la_tc2_eligible(N, head_dim, M)) return 0;
+  if (B <= 0 || H <= 0) return 0;
+  if (!erv::la_tc2_eligible(N, head_dim, M)) {
+    // long sequences (one pair per 128-token tile): [Dh+1][Mp] per pair, Mp = 64 / 128 / 256
+    if (!erv::la_tc_eligible(N, head_dim, M)) return 0;
+    return (size_t)B * H * (head_dim + 1) * (M <= 64 ? 64 : (M <= 128 ? 128 : 256));
+  }
   // the pipelined kernels also keep three per-token statistics (normaliser, exponent shifts of the query / key rows)
   const size_t aux = erv::la_pipe_eligible(N, head_dim, M) ? (size_t)3 * B * N * H : 0;
   return (size_t)B * H * (head_dim + 1) * erv::tc2_mp(M) + aux;
@@ -483,7 +488,7 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
   if (!bwd && la_tc2_eligible(N, DH, M))
     return la_tc2_forward(qkv, out, omega, B, N, H, M, kind, rot, ta, tb, dtype, state, st);
   if (!bwd && la_tc_eligible(N, DH, M))
-    return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, st);
+    return la_tc_forward(qkv, out, omega, B, N, H, DH, M, kind, rot, ta, tb, dtype, state, st);
   static const bool tc_bwd_off = getenv("ERV_DISABLE_TC_BWD") != nullptr, tc2_bwd_off = getenv("ERV_DISABLE_TC2_BWD") != nullptr;
   if (bwd && la_tc_eligible(N, DH, M) && !tc_bwd_off) {
     const int slots = la_slots(B, H);
@@ -494,7 +499,9 @@ static int la_launch(bool bwd, const void* qkv, void* out, const void* dout, voi
       return la_pipe_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
     if (la_tc2_eligible(N, DH, M) && !tc2_bwd_off)
       return la_tc2_backward(qkv, out, dout, dqkv, omega, B, N, H, M, kind, rot, ta, tb, dgp, slots, dtype, state, st);
-    return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype, st);
+    // a state written by the short-sequence forward kernels has their layout: the long-sequence backward then rebuilds S
+    return la_tc_backward(qkv, out, dout, dqkv, omega, B, N, H, DH, M, kind, rot, ta, tb, dgp, slots, dtype,
+                          la_tc2_eligible(N, DH, M) ? nullptr : state, st);
   }
   LaArgs a;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.wt = (const float*)ws; a.ta = ta; a.tb = tb;

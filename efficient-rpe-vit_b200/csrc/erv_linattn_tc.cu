@@ -285,6 +285,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_fwd_kernel(const LaTcArgs
               for (int e = 0; e < 8; ++e) ch[e] = sv[8 * c + e];
               store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
             }
+            if (p.state != nullptr) {  // [S|z] of this pair, d-major: a warp writes 128-byte lines; the backward skips its K1 sweep
+              float* so = p.state + (size_t)pair * (DH + 1) * Mp + f;
+#pragma unroll
+              for (int d = 0; d <= DH; ++d) so[(size_t)d * Mp] = sv[d];
+            }
           }
         }
         fence_before_sync();
@@ -316,13 +321,13 @@ bool la_tc_eligible(int N, int DH, int M) {
 }
 
 int la_tc_forward(const void* qkv, void* out, const float* omega, int B, int N, int H, int DH, int M, int kind, int rot,
-                  const float* ta, const float* tb, int dtype, cudaStream_t st) {
+                  const float* ta, const float* tb, int dtype, float* state, cudaStream_t st) {
   LaTcArgs a;
   a.qkv = qkv; a.out = out; a.omega = omega; a.ta = ta; a.tb = tb;
   a.B = B; a.N = N; a.H = H; a.M = M; a.Mp16 = M <= 64 ? 64 : (M <= 128 ? 128 : 256); a.kind = kind; a.rot = rot;
   a.prescale = (float)pow((double)DH, -0.25);
   a.inv_sqrt_m = (float)(1.0 / sqrt((double)M));
-  a.state = nullptr;
+  a.state = state;
   const size_t smem = la_tc_smem_bytes(DH, a.Mp16);
   int grid = (kNumSMs / H) * H;  // multiple of H: each CTA stays on one head (W images staged once)
   if (grid < H) grid = H;

@@ -25,6 +25,7 @@ struct LaTcBwdArgs {
   const float* ta;
   const float* tb;
   float* dg_part;  // [H][slots][N][DH], circulant only
+  const float* state;  // optional [B*H][DH+1][Mp]: [S|z] saved by la_tc_fwd_kernel; the K1 sweep is skipped when present
   int B, N, H, M, Mp, kind, rot, slots;
   float prescale, inv_sqrt_m;
   long long* trace;  // optional: CTA 0 / thread 0 stamps clock64() at phase boundaries (erv_debug_set_trace)
@@ -147,7 +148,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) la_tc_bwd_kernel(const LaTcBwdA
     float* dg_slot = (p.rot == ERV_ROT_CIRCULANT && p.dg_part)
                          ? p.dg_part + ((size_t)h * p.slots + blockIdx.x / p.H) * N * DH : nullptr;
 
-    for (int pass = 0; pass < 3; ++pass) {  // 0: K1 (build S), 1: Q (dS, dq), 2: K2 (dv, dk)
+    if (p.state != nullptr) {  // [S|z] from the forward instead of the K1 sweep: straight into the bf16 images and z_s
+      if (part < nrb && row < HF) {
+        const int f = part * HF + row;
+        const float* so = p.state + (size_t)pair * (DH + 1) * Mp + f;
+        float sv[DH + 1];
+#pragma unroll
+        for (int d = 0; d <= DH; ++d) sv[d] = __ldg(so + (size_t)d * Mp);
+#pragma unroll
+        for (int c = 0; c < ND / 8; ++c) {
+          float ch[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ch[e] = (8 * c + e <= DH) ? sv[(8 * c + e <= DH) ? 8 * c + e : 0] : 0.f;
+          store_split8(s1, s2, c * s_ch + (f >> 3) * 128 + (f & 7) * 16, ch);
+        }
+        z_s[f] = sv[DH];
+      }
+      fence_smem_to_async();
+      fence_before_sync();
+      __syncthreads();
+    }
+    for (int pass = p.state != nullptr ? 1 : 0; pass < 3; ++pass) {  // 0: K1 (build S), 1: Q (dS, dq), 2: K2 (dv, dk)
       const int which = (pass == 1) ? 0 : 1;
       const T* xb = qkv + qkv_off(b, 0, which, h, N, p.H, DH);
       const T* vb = qkv + qkv_off(b, 0, 2, h, N, p.H, DH);
@@ -589,8 +610,9 @@ size_t la_tc_bwd_smem_bytes(int DH, int M) {
 
 int la_tc_backward(const void* qkv, const void* out, const void* dout, void* dqkv, const float* omega, int B, int N,
                    int H, int DH, int M, int kind, int rot, const float* ta, const float* tb, float* dg_part, int slots,
-                   int dtype, cudaStream_t st) {
+                   int dtype, const float* state, cudaStream_t st) {
   LaTcBwdArgs a;
+  a.state = state;
   a.qkv = qkv; a.out = out; a.dout = dout; a.dqkv = dqkv; a.omega = omega; a.ta = ta; a.tb = tb; a.dg_part = dg_part;
   a.B = B; a.N = N; a.H = H; a.M = M; a.Mp = tc_bwd_mp(M); a.kind = kind; a.rot = rot; a.slots = slots;
   a.prescale = (float)pow((double)DH, -0.25);

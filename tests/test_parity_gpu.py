@@ -178,20 +178,23 @@ def test_attention_matches_oracle(a, r, b, n, dim, heads, m):
             assert_close(p.grad, l.grad, TOL_F32, "d rpe parameter")
 
 
-def test_linear_backward_without_saved_state(monkeypatch):
-    """The short-sequence backward gives the same gradients whether it reads the forward's saved [S|z] or rebuilds it."""
+@pytest.mark.parametrize("b,n,m,dtype", [(7, 65, 256, torch.float32), (3, 197, 44, torch.float32), (2, 300, 200, torch.float32),
+                                         (3, 197, 44, torch.bfloat16)])
+def test_linear_backward_without_saved_state(monkeypatch, b, n, m, dtype):
+    """The tensor-core backward gives the same gradients whether it reads the forward's saved [S|z] or rebuilds it (short
+    sequences: erv_linattn_pipe / tc2; N > 65: erv_linattn_tc, where the saved state replaces the K1 sweep)."""
     from erv_b200 import FAVORPlusAttention, ops
     torch.manual_seed(5)
-    attn = FAVORPlusAttention(32, 2, num_features=256).to(DEV)
-    qkv = torch.randn(7, 65, 96, device=DEV)
-    w = torch.randn(7, 65, 32, device=DEV)
+    attn = FAVORPlusAttention(32, 2, num_features=m).to(DEV)
+    qkv = torch.randn(b, n, 96, device=DEV).to(dtype)
+    w = torch.randn(b, n, 32, device=DEV).to(dtype)
     grads = []
     for save in (True, False):
         monkeypatch.setattr(ops, "SAVE_KV_STATE", save)
         q = qkv.clone().requires_grad_(True)
         (ops.linear_attention(q, attn.omega, 2, ops.FEAT_FAVOR) * w).sum().backward()
-        grads.append(q.grad)
-    assert rel_l2(grads[0], grads[1]) < 1e-5
+        grads.append(q.grad.float())
+    assert rel_l2(grads[0], grads[1]) < (1e-5 if dtype == torch.float32 else 2e-2)
 
 
 def test_softmax_mask_and_return_attention():
