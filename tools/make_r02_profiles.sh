@@ -4,9 +4,10 @@
 TAG=${1:-r02f}
 G=gpurun_out
 HEAD=$(git rev-parse --short HEAD)
-python tools/ncu_summary.py $G/prof_${TAG}_fwd.ncu-rep $G/prof_${TAG}_bwd.ncu-rep $G/prof_${TAG}_l4bwd.ncu-rep > /tmp/sum_lin.md
-python tools/ncu_summary.py $G/prof_${TAG}_k3fwd.ncu-rep $G/prof_${TAG}_k3bwd.ncu-rep $G/prof_${TAG}_k5fwd.ncu-rep $G/prof_${TAG}_k5bwd.ncu-rep > /tmp/sum_k.md
-python tools/ncu_summary.py $G/prof_${TAG}_s4fwd.ncu-rep $G/prof_${TAG}_s4bwd.ncu-rep > /tmp/sum_s.md
+rep() { local f=$G/prof_${TAG}_$1.ncu-rep; [ -f $f ] || f=$G/prof_r02i_$1.ncu-rep; echo $f; }  # kernels unchanged since r02i were not re-captured
+python tools/ncu_summary.py $(rep fwd) $(rep bwd) $(rep l4bwd) > /tmp/sum_lin.md
+python tools/ncu_summary.py $(rep k3fwd) $(rep k3bwd) $(rep k5fwd) $(rep k5bwd) > /tmp/sum_k.md
+python tools/ncu_summary.py $(rep s4fwd) $(rep s4bwd) > /tmp/sum_s.md
 python tools/ncu_summary.py $G/prof_r02_kfft.ncu-rep > /tmp/sum_fft.md
 {
 echo "# Round 2: ncu --set full of the linear-attention kernels (B200, clocks free, evidence set $TAG)"
@@ -19,10 +20,10 @@ echo
 echo "Round 1 for comparison (profiles/r01_final_ncu_attention.md): forward 105 us, tensor pipe 11 %, XU 18 %, issue 34 %; backward 286 us, tensor pipe 6 %, issue 35 %, no_inst the top stall (16 %)."
 echo
 echo "## Warp-stall samples by reason (source page, all lines)"
-for t in fwd bwd; do echo; echo "### la_pipe_${t}_kernel"; echo '```'; python tools/ncu_stalls.py $G/prof_${TAG}_$t.ncu-rep; echo '```'; done
+for t in fwd bwd; do echo; echo "### la_pipe_${t}_kernel"; echo '```'; python tools/ncu_stalls.py $(rep $t); echo '```'; done
 echo
 echo "## Top source lines by stall samples"
-for t in fwd bwd; do echo; echo "### la_pipe_${t}_kernel"; echo '```'; python tools/ncu_lines.py $G/prof_${TAG}_$t.ncu-rep 14; echo '```'; done
+for t in fwd bwd; do echo; echo "### la_pipe_${t}_kernel"; echo '```'; python tools/ncu_lines.py $(rep $t) 14; echo '```'; done
 echo
 echo "Reading: the tensor pipe went from 6 % to 17 % active in the backward and from 11 % to 19 % in the forward; the issue slots are 46-52 % busy."
 echo "The largest single stall site of the backward is the MMA-completion wait of the compute warps (\`mbar_try_wait\`, ~14 % of samples, counted as long_scoreboard);"

@@ -5,8 +5,9 @@ TAG=${1:-r02a}
 mkdir -p gpurun_out
 python bench.py --steps 100 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { tail -5 gpurun_out/bench_$TAG.err; exit 1; }
 tail -1 gpurun_out/bench_$TAG.json | cut -c1-300
-cap() {  # kernel-regex tag skip bench-args...
+cap() {  # kernel-regex tag skip bench-args...   (tags listed in $ERV_SKIP_CAPS are not captured: gpurun returns at most 64 MiB)
   local k=$1 t=$2 s=$3; shift 3
+  case " $ERV_SKIP_CAPS " in *" $t "*) return;; esac
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs "$@" > gpurun_out/plain_${TAG}_$t.log 2>&1 || { echo "plain $t failed"; return; }
   ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -f -o gpurun_out/prof_${TAG}_$t python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs "$@" > gpurun_out/ncu_${TAG}_$t.log 2>&1
 }
