@@ -2,9 +2,9 @@
 // models/attention/favor_plus.py:221-260): D1 = C (phi_k (x) v), D2 = C phi_k by FFT along the patch axis, fused with the
 // read-out num = phi_q . D1, den = phi_q . D2, out = num / (den + 1e-6).  C[i][j] = exp(b[j - i]) is Toeplitz.
 //
-// Route for long sequences (2048 < N - 1 <= 4096; M > 64 or at least 16 (batch, head) pairs), chosen per shape against the tensor-core tile route (erv_ktile_tc.cu)
-// by measurement (profiles/r02_kerple_fft_vs_tile.md).  One 8192-point complex FFT lives entirely in the registers of a
-// 512-thread CTA (16 points per thread) and crosses shared memory twice:
+// Route for long sequences (2048 < N - 1 <= 4096; M > 64 or at least 16 (batch, head) pairs), chosen per shape against the
+// tensor-core tile route (erv_ktile_tc.cu) by measurement (profiles/r02_kerple_fft_vs_tile.md).  One 8192-point complex FFT
+// lives entirely in the registers of a 512-thread CTA (16 points per thread) and crosses shared memory twice:
 //
 //   * the CLS token is split off, so the 4096 patches need a circular length of 2*4096 - 1 <= 8192 (a power of two);
 //     its row and column are rank-1 terms added by the finalize kernels;
@@ -20,7 +20,10 @@
 //     ([B, H, N, M, Dh] in the reference: 49 MB per (batch, head) at N = 4097, M = 44) are never materialised.
 //
 // A CTA owns (batch*head, value column d, chunk of feature pairs); chunk partials are summed in a fixed order by
-// kfft_finalize_kernel, which also adds the CLS column and divides; kfft_cls_kernel computes the CLS row directly.
+// kfft_finalize_kernel, which also adds the CLS column and divides; kfft_cls_kernel computes the CLS row in 32 partial sums.
+// phi_q / phi_k come from the feature-map kernels (fp32 rows in the workspace) and are re-laid out feature-pair-major by
+// kfft_transpose_kernel, so that a CTA stages the 32 KB it needs per feature pair with coalesced 16-byte cp.async; the
+// 64 KB of filter coefficients of the head stay in shared memory.  A numpy model of the algorithm: tests/test_kfft_model.py.
 #include <math.h>
 
 #include "erv_common.cuh"
