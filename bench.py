@@ -337,13 +337,16 @@ def measure(wname, B, steps, warmup, env, do_e2e=True, use_graph=True):
         t0 = time.perf_counter()
         trainer.prefetch(*host_pool[0])
         seen = 0.0
+        sync_every_step = bool(os.environ.get("ERV_E2E_SYNC"))
         for i in range(n_e2e):
             l = trainer.step_prefetched()
             loss_host[i % 2].copy_(l, non_blocking=True)  # device -> pinned host, right behind the step
             loss_ready[i % 2].record()
             if i + 1 < n_e2e:
                 trainer.prefetch(*host_pool[(i + 1) % len(host_pool)])
-            if i > 0:  # the caller reads EVERY step's loss; the read of step i-1 happens while step i runs (an asynchronous logger)
+            if sync_every_step:  # ERV_E2E_SYNC=1: wait for this step's loss before launching the next step
+                loss_ready[i % 2].synchronize()
+            elif i > 0:  # the caller reads EVERY step's loss; the read of step i-1 happens while step i runs (an asynchronous logger)
                 loss_ready[(i - 1) % 2].synchronize()
                 seen += float(loss_host[(i - 1) % 2])
         loss_ready[(n_e2e - 1) % 2].synchronize()
