@@ -408,3 +408,31 @@ def test_kerple_fft_route_matches_oracle(a, b, n, dim, heads, m, kerple_fft_forc
         want = O.attention_forward(x, dict(attn.state_dict()), heads, ATTN_KIND[a], "kerple", dict(rpe.state_dict()), route="dense")
         got = attn.to(DEV).eval()(x.to(DEV), rpe=rpe.to(DEV))
     assert_close(got, want, TOL_F32, "out")
+
+
+def test_kerple_default_dispatch_with_many_pairs_takes_the_fft_route():
+    """16 (batch, head) pairs at 2059 patches: the default dispatch (no forcing) sends the forward to the FFT route (three chunks
+    of feature pairs per CTA column) and the backward to the tiles; outputs and gradients against the oracle's dense route."""
+    from erv_b200 import ATTENTION_REGISTRY, RPE_REGISTRY, _capi
+    from oracle import erv_oracle as O
+    lib = _capi.load()
+    b, n, dim, heads, m = 8, 2060, 32, 2, 44
+    assert lib.erv_kerple_attention_workspace(b, n, heads, dim // heads, m, 0) > lib.erv_kerple_attention_workspace(2, n, heads, dim // heads, m, 0) * 4
+    torch.manual_seed(11)
+    attn = ATTENTION_REGISTRY["favor_plus"](dim=dim, heads=heads, dropout=0.0, num_features=m)
+    rpe = RPE_REGISTRY["most_general"](num_patches=n, dim=dim, heads=heads)
+    with torch.no_grad():
+        rpe.rel_pos_bias.normal_(0.0, 0.3)
+    x, w = torch.randn(b, n, dim), torch.randn(b, n, dim)
+    params = {k: v.clone() for k, v in attn.state_dict().items()}
+    bias = rpe.rel_pos_bias.detach().clone().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    want = O.attention_forward(xo, params, heads, "favor", "kerple", {"rel_pos_bias": bias}, route="dense")
+    (want * w).sum().backward()
+    attn, rpe = attn.to(DEV).eval(), rpe.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    got = attn(xg, rpe=rpe)
+    (got * w.to(DEV)).sum().backward()
+    assert_close(got, want, TOL_F32, "out")
+    assert_close(xg.grad, xo.grad, TOL_F32, "dx")
+    assert_close(rpe.rel_pos_bias.grad, bias.grad, TOL_F32, "d rel_pos_bias")
