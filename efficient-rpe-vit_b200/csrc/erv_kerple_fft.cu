@@ -27,9 +27,14 @@
 #include <math.h>
 
 #include "erv_common.cuh"
+#include "erv_umma.cuh"
 
 namespace erv {
 namespace kfft {
+using umma::mbar_init;
+using umma::mbar_init_fence;
+using umma::mbar_wait;
+using umma::smem_u32;
 
 constexpr int L = 8192;        // transform length
 constexpr int NT = 512;        // threads per CTA: 16 points each
@@ -231,32 +236,45 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
     vv[r] = 0.f;
     if (i < NP) vv[r] = d < p.DH ? to_f(static_cast<const T*>(p.qkv)[qkv_off(b, i + 1, 2, h, N, p.H, p.DH) + d]) : 1.f;
   }
-  // phi_k[., m..m+1] of the next feature pair and phi_q[., m..m+1] of the current one are staged with coalesced 16-byte
-  // cp.async from the feature-pair-major copies (kfft_transpose_kernel) while the transforms run; the filter coefficients of
-  // this head stay in shared memory for the whole CTA.  (First version: 8-byte strided copies straight from the token-major
-  // rows and 16 __ldg of G per transform -- 38 % of the warp-stall samples were long_scoreboard on exactly those two lines.)
+  // phi_k[., m..m+1] of the next feature pair, phi_q[., m..m+1] of the current one and the filter coefficients of this head are
+  // brought into shared memory by the TMA unit as bulk copies (cp.async.bulk, one instruction per 32 / 64 KB row, completion on
+  // an mbarrier) from the feature-pair-major copies (kfft_transpose_kernel) while the transforms run.  (First version: 8-byte
+  // strided cp.async from the token-major rows and 16 __ldg of G per transform -- 38 % of the warp-stall samples were
+  // long_scoreboard on exactly those two lines; second version: per-thread 16-byte cp.async + two CTA barriers per feature pair.)
   float2* stage_k = sm + 256 * XROW;
   float2* stage_q = stage_k + NP_MAX;
   float2* Gs = stage_q + NP_MAX;
+  __shared__ __align__(8) uint64_t bar_k, bar_q, bar_g;
   const int NPp = p.NPp;
-  auto stage = [&](float2* dst, const float2* src) {  // NPp float2 = NPp / 2 chunks of 16 bytes
-    for (int c = t; c < NPp / 2; c += NT)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 2 * c)),
-                   "l"(src + 2 * c) : "memory");
+  const uint32_t row_bytes = (uint32_t)NPp * sizeof(float2);  // NPp is even: a multiple of 16 bytes
+  auto bulk = [&](float2* dst, const float2* src, uint32_t bytes, uint64_t* bar) {  // one thread
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
   };
   const int fp0 = chunk * p.fp_per_chunk, fp1 = min(fp0 + p.fp_per_chunk, (p.M + 1) / 2);
   const float2* tq = p.phiT_q + (size_t)pair * (ld / 2) * NPp;
   const float2* tk = p.phiT_k + (size_t)pair * (ld / 2) * NPp;
-  for (int c = t; c < L / 2; c += NT)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(Gs + 2 * c)),
-                 "l"(G + 2 * c) : "memory");
-  if (fp0 < fp1) stage(stage_k, tk + (size_t)fp0 * NPp);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  if (t == 0) {
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_q, 1);
+    mbar_init(&bar_g, 4);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int c = 0; c < 4; ++c)  // 4 x 16 KB: a single 64 KB cp.async.bulk faults (illegal address) on this driver, 32 KB rows are fine
+      bulk(Gs + c * (L / 4), G + c * (L / 4), (uint32_t)(L / 4 * sizeof(float2)), &bar_g);
+    if (fp0 < fp1) bulk(stage_k, tk + (size_t)fp0 * NPp, row_bytes, &bar_k);
+  }
+  uint32_t ph_k = 0, ph_q = 0;
+  if (fp0 < fp1) mbar_wait(&bar_g, 0);
   for (int fp = fp0; fp < fp1; ++fp) {
     const bool two = 2 * fp + 1 < p.M;
     float2 x[16];
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();  // phi_k of this feature pair (and, the first time, G) copied by all threads
+    mbar_wait(&bar_k, ph_k);  // phi_k of this feature pair has landed
+    ph_k ^= 1;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;
@@ -268,17 +286,18 @@ __global__ void __launch_bounds__(NT, 1) kfft_fwd_kernel(const FftArgs p) {
     }
     fft8192(x, sm, w);
     // every thread is past its stage_k / stage_q reads (the transform synchronises the CTA): refill both
-    if (fp + 1 < fp1) stage(stage_k, tk + (size_t)(fp + 1) * NPp);
-    stage(stage_q, tq + (size_t)fp * NPp);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (t == 0) {
+      if (fp + 1 < fp1) bulk(stage_k, tk + (size_t)(fp + 1) * NPp, row_bytes, &bar_k);
+      bulk(stage_q, tq + (size_t)fp * NPp, row_bytes, &bar_q);
+    }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const float2 y = cmul(x[q], Gs[t + 512 * q]);
       x[q] = make_float2(y.x, -y.y);  // inverse transform as conj(DFT(conj(.)))
     }
     fft8192(x, sm, w);
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();  // phi_q of this feature pair
+    mbar_wait(&bar_q, ph_q);  // phi_q of this feature pair
+    ph_q ^= 1;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = t + 512 * r;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // One lane of a CONVERGED warp (all 32 lanes must execute this).  Issue tcgen05.mma / commit under `if (elect_one())` inside a
 // warp-uniform branch: ptxas then emits a plain predicated UTCHMMA.  Under a divergent `if (tid == 0)` it wraps every MMA in an
 // ELECT / BRA.U.ANY loop whose branch waits on the instruction's scoreboard (measured: ~100-130 SM cycles per MMA of issue time
-// however narrow the MMA, profiles/r02_tcgen05_issue_cost.md).
+// however narrow the MMA, profiles/r02_tcgen05_mma_cost.md).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
