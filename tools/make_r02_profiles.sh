@@ -64,8 +64,8 @@ echo
 echo "Per (batch, head) pair the FFT route runs M (Dh + 1) / 2 complex column pairs (two real columns per transform), each one forward and one"
 echo "inverse 8192-point transform: 748 transforms at M = 44, 4352 at M = 256, independent of N up to 4097.  One transform is"
 echo "3 x 16-point DFTs + 2 twiddle passes per thread (512 threads x 16 points) and two shared-memory exchanges of 64 KB: ~1000 thread"
-echo "instructions, ~4.5 k cycles measured (7.9 k before the phi rows were staged with coalesced cp.async and the filter kept in shared memory)."
-echo "At 148 SMs that is 748 x 4.5 k / 148 = 23 k cycles = 11.6 us per pair at M = 44 when the grid is full; measured 23.7 us at 64 pairs including"
+echo "instructions, ~4.2 k cycles measured (7.9 k before the phi rows were staged as bulk copies from feature-pair-major rows and the filter kept in shared memory)."
+echo "At 148 SMs that is 748 x 4.2 k / 148 = 21 k cycles = 10.8 us per pair at M = 44 when the grid is full; measured 22.7 us at 64 pairs including"
 echo "the feature maps and the finalize kernels.  The tile route does 2 N^2 (M + Dh) FLOP per pair on the tensor pipe (2.05 GFLOP at N = 4097,"
 echo "M = 44: 3.7 us at the bf16 peak with the three-term split) but spends ~5 us per 128 x 128 tile with its phases serialised: 35.8 us per pair."
 echo "For M > 64 the tile route has no tcgen05 instance and runs on CUDA cores (510 us per pair at M = 256)."
@@ -78,8 +78,8 @@ echo '```'
 python tools/ncu_stalls.py $G/prof_r02_kfft.ncu-rep
 echo '```'
 echo
-echo "Achieved HBM throughput is ~1 % of peak and the tensor pipe is idle: the kernel is bound by fp32 instruction issue (issue slots 69 % busy, FMA pipe 54 %,"
-echo "not_selected the top stall reason, one 16-warp CTA per SM at 128 registers); phi rows are staged from L2 with cp.async, the filter coefficients stay in shared memory (long_scoreboard 38 % -> 1.6 %)."
+echo "Achieved HBM throughput is ~1 % of peak and the tensor pipe is idle: the kernel is bound by fp32 instruction issue (issue slots 70 % busy, FMA pipe 58 %,"
+echo "not_selected the top stall reason, one 16-warp CTA per SM at 128 registers); phi rows are staged from L2 by the TMA unit (cp.async.bulk + mbarrier, UBLKCP in SASS), the filter coefficients stay in shared memory (long_scoreboard 38 % -> 1.8 %)."
 } > profiles/r02_kerple_fft_vs_tile.md
 python tools/ll_summary.py $G/launches_$TAG.csv 30 > /tmp/ll.txt
 {
