@@ -31,19 +31,12 @@ __device__ __forceinline__ uint32_t rn_bf16_word(float v) { return (__float_as_u
 __device__ __forceinline__ void store_split8_3(uint8_t* hi_img, uint8_t* lo_img, uint8_t* lo2_img, uint32_t off, const float (&v)[8]) {
   uint32_t h[4], l[4], m[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t hb[2], lb[2], mb[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float x = v[2 * i + e];
-      hb[e] = rn_bf16_word(x);
-      const float r = x - __uint_as_float(hb[e]);
-      lb[e] = rn_bf16_word(r);
-      mb[e] = __float_as_uint(r - __uint_as_float(lb[e])) + 0x8000u;
-    }
-    h[i] = __byte_perm(hb[0], hb[1], 0x7632);
-    l[i] = __byte_perm(lb[0], lb[1], 0x7632);
-    m[i] = __byte_perm(mb[0], mb[1], 0x7632);
+  for (int i = 0; i < 4; ++i) {  // two values per F2FP (cvt.rn.bf16x2.f32): 12 instructions per pair instead of 17 integer ones
+    const float a = v[2 * i], b = v[2 * i + 1];
+    h[i] = pack_bf16x2_rn(a, b);
+    const float ra = a - __uint_as_float(h[i] << 16), rb = b - __uint_as_float(h[i] & 0xffff0000u);
+    l[i] = pack_bf16x2_rn(ra, rb);
+    m[i] = pack_bf16x2_rn(ra - __uint_as_float(l[i] << 16), rb - __uint_as_float(l[i] & 0xffff0000u));
   }
   *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(l[0], l[1], l[2], l[3]);

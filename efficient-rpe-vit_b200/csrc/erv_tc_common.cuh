@@ -179,7 +179,7 @@ __device__ __forceinline__ void store_x_images(uint8_t* xh, uint8_t* xl, const f
 // hi = bf16(v) and lo = bf16(v - hi), both round-to-nearest, two values per 32-bit word: hi + lo carries >= 16 significant bits
 // (|v - hi| <= 2^-9 |v| is exact in fp32, its own rounding error is <= 2^-18 |v|).  Six instructions per pair of values:
 // two F2FP.BF16.F32.PACK_AB, a shift, a mask and two subtractions.  F2FP runs at 32 lanes/clk/SM on a pipe of its own: it does
-// not compete with MUFU.EX2 (profiles/r02_tcgen05_issue_cost.md), unlike the round-1 integer version (eight ALU instructions).
+// not compete with MUFU.EX2 (profiles/r02_tcgen05_mma_cost.md), unlike the round-1 integer version (eight ALU instructions).
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo_half, float hi_half) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
