@@ -4,7 +4,7 @@
 TAG=${1:-r02f}
 G=gpurun_out
 HEAD=$(git rev-parse --short HEAD)
-rep() { local f=$G/prof_${TAG}_$1.ncu-rep; [ -f $f ] || f=$G/prof_r02i_$1.ncu-rep; echo $f; }  # kernels unchanged since r02i were not re-captured
+rep() { local f=$G/prof_${TAG}_$1.ncu-rep; [ -f $f ] || f=$G/prof_r02j_$1.ncu-rep; [ -f $f ] || f=$G/prof_r02i_$1.ncu-rep; echo $f; }  # kernels unchanged since r02i were not re-captured
 python tools/ncu_summary.py $(rep fwd) $(rep bwd) $(rep l4bwd) > /tmp/sum_lin.md
 python tools/ncu_summary.py $(rep k3fwd) $(rep k3bwd) $(rep k5fwd) $(rep k5bwd) > /tmp/sum_k.md
 python tools/ncu_summary.py $(rep s4fwd) $(rep s4bwd) > /tmp/sum_s.md
